@@ -1,0 +1,83 @@
+// Shared device/host helpers for libinsider_b200 (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace ib {
+
+constexpr int WARP = 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int KMAX = 32;           // latent_dim limit: one lane per coordinate in the per-gene solver
+constexpr int TG = 16;             // genes per streamed tile (two 8-wide DMMA n-tiles)
+
+// Pitches: a leading dimension p with p % 8 == 4 makes every DMMA fragment load (address = t*p + g or g*p + t,
+// g in 0..7, t in 0..3) bank-conflict-free for 64-bit shared-memory accesses.
+__host__ __device__ inline int pitch4(int n) { int p = (n + 7) / 8 * 8 + 4; return (p - 8 >= n) ? p - 8 : p; }
+__host__ __device__ inline int round_up(int n, int m) { return (n + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// counter-based permutation source (mode B) — must match oracle/insider_oracle.cpp:randperm bit-for-bit
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t perm_key(uint64_t seed, uint32_t als_iter, uint64_t gene, uint32_t draw) {
+    return mix64(seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter)) ^
+           mix64(gene * 0xD1B54A32D192ED03ull + (uint64_t)draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+}
+__host__ __device__ inline uint32_t perm_value(uint64_t key, int pos) {
+    return (uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(pos + 1)) >> 33);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------
+// warp helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col). Lane l: g = l>>2, t = l&3.
+//   a = A[g][t], b = B[t][g], d0 = D[g][2t], d1 = D[g][2t+1].
+// Measured on B200 (profiles/r01_microbench_fp64_hbm.txt): result == fma(a3,b3,fma(a2,b2,fma(a1,b1,fma(a0,b0,c)))).
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk, 1-D): global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes must be a multiple of 16, src and dst 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace ib

@@ -1,0 +1,515 @@
+// Streaming passes over the N x P expression matrix (HBM-bound by design; FP64 DMMA for the dense contractions).
+//
+//   k_row_b    B_partial = (M o Y) V^T          replaces the per-row gathers + dgemv of src/optimize.cpp:161-171 (tuning=1)
+//                                               and Xtys = V R^T of src/optimize.cpp:180 (tuning=0), in sufficient-statistic form
+//   k_col_xty  Xty = U^T (M o Y)                replaces U[sel,:]^T y[sel] of src/optimize.cpp:216-222 and U^T Y of :235
+//   k_sse      sum m (y - u.v)^2, |V|^2, |V|_1  replaces predict + residual + evaluate + the V terms of compute_loss
+//                                               (src/utils.cpp:52-102, src/optimize.cpp:377-384) as one fused pass
+//
+// All three stream tiles of TG = 16 genes x R rows through shared memory with cp.async.bulk (TMA 1-D bulk copies)
+// completing on mbarriers, NSTAGE deep, and contract them with mma.sync m8n8k4 f64 (DMMA). Pitches are chosen
+// (pitch % 8 == 4) so every fragment load is bank-conflict free. Accumulation order is fixed => bitwise reproducible.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ib {
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int NWARPS = 8;
+constexpr int MT_PER_WARP = 6;          // 8 warps x 6 m-tiles x 8 rows = 384 rows per slab
+constexpr int SLAB_ROWS_BIG = 384;      // k_row_b multi-slab
+constexpr int SLAB_ROWS_SMALL = 128;    // k_col_xty / k_sse multi-slab
+constexpr int SINGLE_SLAB_MAX_N = 384;     // 48 m-tiles of 8 rows
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+struct StreamArgs {
+    const double* Y; const uint32_t* trC; const uint32_t* teC; const double* V; const double* Ut;
+    double* out;                 // Bp / Xty / partial
+    int N, K, KP, ldY, ldV, ldT, Wp;
+    int n_tiles;                 // gene tiles in total
+    int R, n_slabs, pitchS, pitchU;
+    int n_stages;
+    int n_splits;                // k_row_b: gene splits (grid.x); others: number of blocks
+};
+
+// balanced partition of n items over parts
+__device__ __forceinline__ void split_range(int n, int parts, int idx, int& b, int& e) {
+    int q = n / parts, r = n % parts;
+    b = idx * q + min(idx, r);
+    e = b + q + (idx < r ? 1 : 0);
+}
+
+// zero the masked-out entries of a landed Y piece: thread (c = tid/16, w = tid%16) owns word w of gene c
+__device__ __forceinline__ void premask(double* Ys, int pitchS, uint32_t word, int w, int c, int rows_here) {
+    int base = 32 * w;
+    if (base >= rows_here) return;
+    uint32_t z = ~word;
+    int lim = rows_here - base;
+    if (lim < 32) z &= (1u << lim) - 1u;
+    while (z) {
+        int b = __ffs(z) - 1;
+        z &= z - 1;
+        Ys[c * pitchS + base + b] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_row_b: grid (n_splits, n_slabs). Each block accumulates B[rows of its slab][K] over its gene tiles.
+template <int NT, bool MASKED>
+__global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int slab = blockIdx.y, r0 = slab * a.R;
+    const int rows_here = min(a.R, a.ldY - r0);
+    const int mt_here = (min(a.N - r0, a.R) + 7) / 8;
+    int t0, t1;
+    split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
+    const int n_items = t1 - t0;
+
+    const int ysz = TG * a.pitchS + 8;       // doubles per Y piece (+slack for the 8-row tile overhang)
+    const int vsz = TG * a.ldV;
+    const int stage_doubles = ysz + vsz;
+    double* stage0 = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)a.n_stages * stage_doubles);
+    const int S = a.n_stages;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    // slack doubles are never written by TMA: zero them once so overhang rows read finite values
+    for (int s = tid; s < S * 8; s += THREADS) stage0[(size_t)(s / 8) * stage_doubles + TG * a.pitchS + (s % 8)] = 0.0;
+    __syncthreads();
+
+    auto issue = [&](int item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        double* Vs = Ys + ysz;
+        const int64_t gene = (int64_t)(t0 + item) * TG;
+        const uint32_t ybytes = (uint32_t)rows_here * 8u;
+        mbar_expect_tx(&bars[s], ybytes * TG + (uint32_t)vsz * 8u);
+        if (a.pitchS == a.ldY && rows_here == a.ldY) {
+            tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
+        } else {
+            for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
+        }
+        tma_load_1d(Vs, a.V + gene * a.ldV, (uint32_t)vsz * 8u, &bars[s]);
+    };
+    if (tid == 0) for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
+
+    double acc[MT_PER_WARP][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT_PER_WARP; ++i)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+
+    for (int item = 0; item < n_items; ++item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        const double* Vs = Ys + ysz;
+        if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
+        uint32_t word = 0;
+        if (MASKED) {
+            const int c = tid >> 4, w = tid & 15;
+            if (32 * w < rows_here) word = __ldg(a.trC + ((int64_t)(t0 + item) * TG + c) * a.Wp + (r0 >> 5) + w);
+        }
+        mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
+        if (MASKED) {
+            premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int ks = 0; ks < TG / 4; ++ks) {
+            double b[NT];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) b[n] = Vs[(4 * ks + t) * a.ldV + 8 * n + g];
+            const double* yrow = Ys + (4 * ks + t) * a.pitchS + g;
+#pragma unroll
+            for (int i = 0; i < MT_PER_WARP; ++i) {
+                const int mt = warp + NWARPS * i;
+                if (mt < mt_here) {
+                    const double av = yrow[8 * mt];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) dmma(acc[i][n][0], acc[i][n][1], av, b[n]);
+                }
+            }
+        }
+        __syncthreads();   // stage s may be refilled
+    }
+    // store the block's partial: Bp[split][N][KP]
+    double* Bp = a.out + (size_t)blockIdx.x * a.N * a.KP;
+#pragma unroll
+    for (int i = 0; i < MT_PER_WARP; ++i) {
+        const int mt = warp + NWARPS * i;
+        const int row = r0 + 8 * mt + g;
+        if (mt < mt_here && row < a.N) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int k = 8 * n + 2 * t;
+                if (k < a.KP) Bp[(size_t)row * a.KP + k] = acc[i][n][0];
+                if (k + 1 < a.KP) Bp[(size_t)row * a.KP + k + 1] = acc[i][n][1];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_col_xty: grid (n_blocks). Items = (tile, slab) of the block's tile range; reduction over rows is split over warps.
+template <int NT, bool MASKED, bool RESIDENT_U>
+__global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    int t0, t1;
+    split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
+    const int n_items = (t1 - t0) * a.n_slabs;
+    const int S = a.n_stages;
+
+    const int ysz = TG * a.pitchS;
+    const int usz = a.KP * a.pitchU;
+    const int stage_doubles = ysz + (RESIDENT_U ? 0 : usz);
+    double* Ures = reinterpret_cast<double*>(smem_raw);                       // resident Ut (if any)
+    double* stage0 = Ures + (RESIDENT_U ? usz : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)S * stage_doubles);   // S stage barriers + 1 for Ut
+
+    if (tid == 0) {
+        for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        const int64_t gene = (int64_t)tile * TG;
+        const uint32_t ybytes = (uint32_t)rows_here * 8u;
+        uint32_t total = ybytes * TG;
+        if (!RESIDENT_U) total += (uint32_t)a.KP * ybytes;
+        mbar_expect_tx(&bars[s], total);
+        if (a.pitchS == a.ldY && rows_here == a.ldY) {
+            tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
+        } else {
+            for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
+        }
+        if (!RESIDENT_U) {
+            double* Us = Ys + ysz;
+            for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, ybytes, &bars[s]);
+        }
+    };
+    if (tid == 0) {
+        if (RESIDENT_U) {
+            mbar_expect_tx(&bars[S], (uint32_t)usz * 8u);
+            tma_load_1d(Ures, a.Ut, (uint32_t)usz * 8u, &bars[S]);
+        }
+        for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
+    }
+    if (RESIDENT_U) mbar_wait(&bars[S], 0);
+
+    double acc[NT][2][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) acc[n][m][0] = acc[n][m][1] = 0.0;
+
+    for (int item = 0; item < n_items; ++item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
+        uint32_t word = 0;
+        if (MASKED) {
+            const int c = tid >> 4, w = tid & 15;
+            if (32 * w < rows_here) word = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
+        }
+        mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
+        if (MASKED) {
+            premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
+            __syncthreads();
+        }
+        const int KS = rows_here >> 2;
+        int k0, k1;
+        split_range(KS, NWARPS, warp, k0, k1);
+        for (int ks = k0; ks < k1; ++ks) {
+            double av[NT], bv[2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) av[n] = Us[(8 * n + g) * a.pitchU + 4 * ks + t];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) bv[m] = Ys[(8 * m + g) * a.pitchS + 4 * ks + t];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) dmma(acc[n][m][0], acc[n][m][1], av[n], bv[m]);
+        }
+        if (slab == a.n_slabs - 1) {
+            // cross-warp reduction in a fixed order, then store the K x 16 tile of Xty. The scratch
+            // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer.
+            double* scratch = Ys;
+            __syncthreads();
+            double* sc = scratch + warp * (NT * 2 * 64);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[n][m][0];
+                    sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[n][m][1];
+                    acc[n][m][0] = acc[n][m][1] = 0.0;
+                }
+            __syncthreads();
+            for (int x = tid; x < NT * 2 * 64; x += THREADS) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
+                const int tl = x >> 6, ln = (x & 63) >> 1, e = x & 1;
+                const int n = tl >> 1, m = tl & 1;
+                const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
+                if (k < a.ldV) a.out[((int64_t)tile * TG + gene) * a.ldV + k] = sum;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_sse: grid (n_blocks). pred = U V per (tile, slab), residual against the Y piece, masked sums of squares.
+template <int NT, bool MASKED, bool RESIDENT_U>
+__global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    int t0, t1;
+    split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
+    const int n_items = (t1 - t0) * a.n_slabs;
+    const int S = a.n_stages;
+
+    const int ysz = TG * a.pitchS + 8;
+    const int vsz = TG * a.ldV;
+    const int usz = a.KP * a.pitchU;
+    const int stage_doubles = ysz + vsz + (RESIDENT_U ? 0 : usz);
+    double* Ures = reinterpret_cast<double*>(smem_raw);
+    double* stage0 = Ures + (RESIDENT_U ? usz : 0);
+    double* red = stage0 + (size_t)S * stage_doubles;                          // [NWARPS][4]
+    uint32_t* mk = reinterpret_cast<uint32_t*>(red + NWARPS * 4);              // [2][TG][16] mask words (train, test)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(mk + 2 * TG * 16);
+
+    if (tid == 0) {
+        for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        double* Vs = Ys + ysz;
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        const int rows_u = min(a.R, a.ldT - r0);
+        const int64_t gene = (int64_t)tile * TG;
+        const uint32_t ybytes = (uint32_t)rows_here * 8u;
+        uint32_t total = ybytes * TG + (uint32_t)vsz * 8u;
+        if (!RESIDENT_U) total += (uint32_t)a.KP * (uint32_t)rows_u * 8u;
+        mbar_expect_tx(&bars[s], total);
+        if (a.pitchS == a.ldY && rows_here == a.ldY) {
+            tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
+        } else {
+            for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
+        }
+        tma_load_1d(Vs, a.V + gene * a.ldV, (uint32_t)vsz * 8u, &bars[s]);
+        if (!RESIDENT_U) {
+            double* Us = Vs + vsz;
+            for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, (uint32_t)rows_u * 8u, &bars[s]);
+        }
+    };
+    if (tid == 0) {
+        if (RESIDENT_U) {
+            mbar_expect_tx(&bars[S], (uint32_t)usz * 8u);
+            tma_load_1d(Ures, a.Ut, (uint32_t)usz * 8u, &bars[S]);
+        }
+        for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
+    }
+    if (RESIDENT_U) mbar_wait(&bars[S], 0);
+
+    double sse_tr = 0.0, sse_te = 0.0, v2 = 0.0, v1 = 0.0;
+    for (int item = 0; item < n_items; ++item) {
+        const int s = item % S;
+        const double* Ys = stage0 + (size_t)s * stage_doubles;
+        const double* Vs = Ys + ysz;
+        const double* Us = RESIDENT_U ? Ures : (Vs + vsz);
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        const int mt_here = (min(a.N - r0, a.R) + 7) / 8;
+        if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
+        if (MASKED) {
+            const int c = tid >> 4, w = tid & 15;
+            uint32_t wtr = 0, wte = 0;
+            if (32 * w < rows_here) {
+                const int64_t idx = ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w;
+                wtr = __ldg(a.trC + idx);
+                wte = __ldg(a.teC + idx);
+            }
+            mk[tid] = wtr;
+            mk[TG * 16 + tid] = wte;
+        }
+        mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
+        __syncthreads();
+        if (slab == 0) {
+            for (int x = tid; x < vsz; x += THREADS) { const double v = Vs[x]; v2 = fma(v, v, v2); v1 += fabs(v); }
+        }
+        double bv[2][NT * 2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int ks = 0; ks < NT * 2; ++ks) bv[m][ks] = Vs[(8 * m + g) * a.ldV + 4 * ks + t];
+        for (int mt = warp; mt < mt_here; mt += NWARPS) {
+            double p[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int ks = 0; ks < NT * 2; ++ks) {
+                const double av = Us[(4 * ks + t) * a.pitchU + 8 * mt + g];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) dmma(p[m][0], p[m][1], av, bv[m][ks]);
+            }
+            const int lr = 8 * mt + g;              // row within the slab
+            const bool row_ok = (r0 + lr) < a.N;
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gene = 8 * m + 2 * t + e;
+                    const double r = Ys[gene * a.pitchS + lr] - p[m][e];
+                    const double r2 = r * r;
+                    if (MASKED) {
+                        const uint32_t wtr = mk[gene * 16 + (lr >> 5)], wte = mk[TG * 16 + gene * 16 + (lr >> 5)];
+                        if (row_ok && ((wtr >> (lr & 31)) & 1u)) sse_tr += r2;
+                        if (row_ok && ((wte >> (lr & 31)) & 1u)) sse_te += r2;
+                    } else {
+                        if (row_ok) sse_tr += r2;
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    sse_tr = warp_sum(sse_tr); sse_te = warp_sum(sse_te); v2 = warp_sum(v2); v1 = warp_sum(v1);
+    if (lane == 0) { red[warp * 4 + 0] = sse_tr; red[warp * 4 + 1] = sse_te; red[warp * 4 + 2] = v2; red[warp * 4 + 3] = v1; }
+    __syncthreads();
+    if (tid < 4) {
+        double s = 0.0;
+        for (int w = 0; w < NWARPS; ++w) s += red[w * 4 + tid];
+        a.out[(size_t)blockIdx.x * 4 + tid] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+template <typename KernelT>
+void set_smem(KernelT k, size_t bytes) {
+    static thread_local const void* last = nullptr;
+    static thread_local size_t last_bytes = 0;
+    if (last != (const void*)k || last_bytes < bytes) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        last = (const void*)k; last_bytes = bytes;
+    }
+}
+
+StreamArgs base_args(const Geom& g) {
+    StreamArgs a{};
+    a.N = g.N; a.K = g.K; a.KP = g.KP; a.ldY = g.ldY; a.ldV = g.ldV; a.ldT = g.ldT; a.Wp = g.Wp; a.n_tiles = g.n_tiles;
+    return a;
+}
+
+}  // namespace
+
+int row_b_default_splits(const Geom& g, int sm_count) {
+    const int n_slabs = (g.N <= SINGLE_SLAB_MAX_N) ? 1 : (g.ldY + SLAB_ROWS_BIG - 1) / SLAB_ROWS_BIG;
+    int splits = sm_count / n_slabs;
+    if (splits < 1) splits = 1;
+    if (splits > g.n_tiles) splits = g.n_tiles;
+    return splits;
+}
+size_t row_b_partial_elems(const Geom& g, int n_splits) { return (size_t)n_splits * g.N * g.KP; }
+int stream_default_blocks(const Geom& g, int sm_count) { return sm_count < g.n_tiles ? sm_count : g.n_tiles; }
+
+void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, int n_splits,
+                  cudaStream_t st) {
+    StreamArgs a = base_args(g);
+    a.Y = Y; a.trC = trC; a.V = V; a.out = Bp; a.n_splits = n_splits;
+    if (g.N <= SINGLE_SLAB_MAX_N) { a.R = g.ldY; a.n_slabs = 1; a.pitchS = g.ldY; }
+    else { a.R = SLAB_ROWS_BIG; a.n_slabs = (g.ldY + a.R - 1) / a.R; a.pitchS = pitch4(a.R); }
+    const size_t stage = ((size_t)TG * a.pitchS + 8 + (size_t)TG * g.ldV) * 8;
+    int S = (int)((SMEM_LIMIT - 64) / stage);
+    if (S > 4) S = 4;
+    if (S < 2) S = 2;
+    a.n_stages = S;
+    const size_t smem = S * stage + 8 * (S + 1);
+    dim3 grid(n_splits, a.n_slabs);
+#define LAUNCH_RB(NTv)                                                                                         \
+    if (masked) { set_smem(k_row_b<NTv, true>, smem); k_row_b<NTv, true><<<grid, THREADS, smem, st>>>(a); }    \
+    else { set_smem(k_row_b<NTv, false>, smem); k_row_b<NTv, false><<<grid, THREADS, smem, st>>>(a); }
+    switch (g.NT) { case 1: LAUNCH_RB(1) break; case 2: LAUNCH_RB(2) break; case 3: LAUNCH_RB(3) break; default: LAUNCH_RB(4) break; }
+#undef LAUNCH_RB
+}
+
+namespace {
+// geometry shared by k_col_xty and k_sse
+bool resident_geometry(const Geom& g, StreamArgs& a, size_t extra_stage_doubles, size_t fixed_bytes) {
+    const size_t ures = (size_t)g.KP * g.ldT * 8;
+    const size_t stage = ((size_t)TG * g.ldY + extra_stage_doubles) * 8;
+    if (g.N <= SINGLE_SLAB_MAX_N && ures + 2 * stage + fixed_bytes <= SMEM_LIMIT) {
+        a.R = g.ldY; a.n_slabs = 1; a.pitchS = g.ldY; a.pitchU = g.ldT;
+        int S = (int)((SMEM_LIMIT - ures - fixed_bytes) / stage);
+        a.n_stages = S > 4 ? 4 : S;
+        return true;
+    }
+    a.R = SLAB_ROWS_SMALL; a.n_slabs = (g.ldY + a.R - 1) / a.R; a.pitchS = pitch4(a.R); a.pitchU = a.pitchS;
+    const size_t stage2 = ((size_t)TG * a.pitchS + (size_t)g.KP * a.pitchU + extra_stage_doubles) * 8;
+    int S = (int)((SMEM_LIMIT - fixed_bytes) / stage2);
+    a.n_stages = S > 4 ? 4 : (S < 2 ? 2 : S);
+    return false;
+}
+}  // namespace
+
+void launch_col_xty(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* Ut, double* Xty, int n_blocks,
+                    cudaStream_t st) {
+    StreamArgs a = base_args(g);
+    a.Y = Y; a.trC = trC; a.Ut = Ut; a.out = Xty; a.n_splits = n_blocks;
+    const size_t fixed = 8 * 8;
+    const bool res = resident_geometry(g, a, 0, fixed);
+    const size_t stage = ((size_t)TG * a.pitchS + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
+    const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + fixed;
+#define LAUNCH_CX(NTv, M, RS) { set_smem(k_col_xty<NTv, M, RS>, smem); k_col_xty<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a); }
+#define LAUNCH_CX2(NTv)                                                       \
+    if (masked) { if (res) LAUNCH_CX(NTv, true, true) else LAUNCH_CX(NTv, true, false) } \
+    else { if (res) LAUNCH_CX(NTv, false, true) else LAUNCH_CX(NTv, false, false) }
+    switch (g.NT) { case 1: LAUNCH_CX2(1) break; case 2: LAUNCH_CX2(2) break; case 3: LAUNCH_CX2(3) break; default: LAUNCH_CX2(4) break; }
+#undef LAUNCH_CX2
+#undef LAUNCH_CX
+}
+
+void launch_sse(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const uint32_t* teC, const double* Ut, const double* V,
+                double* partial, int n_blocks, cudaStream_t st) {
+    StreamArgs a = base_args(g);
+    a.Y = Y; a.trC = trC; a.teC = teC; a.Ut = Ut; a.V = V; a.out = partial; a.n_splits = n_blocks;
+    const size_t fixed = (size_t)NWARPS * 4 * 8 + 2 * TG * 16 * 4 + 8 * 8;
+    const size_t extra = 8 + (size_t)TG * g.ldV;
+    const bool res = resident_geometry(g, a, extra, fixed);
+    const size_t stage = ((size_t)TG * a.pitchS + extra + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
+    const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + fixed;
+#define LAUNCH_SS(NTv, M, RS) { set_smem(k_sse<NTv, M, RS>, smem); k_sse<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a); }
+#define LAUNCH_SS2(NTv)                                                       \
+    if (masked) { if (res) LAUNCH_SS(NTv, true, true) else LAUNCH_SS(NTv, true, false) } \
+    else { if (res) LAUNCH_SS(NTv, false, true) else LAUNCH_SS(NTv, false, false) }
+    switch (g.NT) { case 1: LAUNCH_SS2(1) break; case 2: LAUNCH_SS2(2) break; case 3: LAUNCH_SS2(3) break; default: LAUNCH_SS2(4) break; }
+#undef LAUNCH_SS2
+#undef LAUNCH_SS
+}
+
+}  // namespace ib

@@ -1,0 +1,110 @@
+// Kernel launch interfaces of libinsider_b200 (definitions in k_*.cu). All pointers are device pointers.
+//
+// Device data layout (see DESIGN.md "Data layout in HBM"):
+//   Y    [P_pad][ldY]   column j = gene j, ldY = pitch4(N) rows, zero padded (rows >= N, genes >= P)
+//   V    [P_pad][ldV]   gene j's K-vector contiguous, ldV = pitch4(KP), KP = round_up(K, 8), zero padded
+//   Xty  [P_pad][ldV]   same layout as V
+//   trC/teC [P_pad][Wp] train/test mask bits, bit (i & 31) of word i>>5 of gene j; Wp = round_up(ceil(N/32), 4)
+//   trR  [N][WPr]       train mask bits transposed: bit (j & 31) of word j>>5 of row i; WPr = ceil(P_pad/32)
+//   U    [N][KP]        row factor, row-major, zero padded columns
+//   Ut   [KP][ldT]      its transpose, ldT = pitch4(round_up(N, 8)), zero padded
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ib {
+
+struct Geom {
+    int N, K, KP, NT;        // NT = KP / 8
+    int ldY, ldV, ldT, Wp, WPr;
+    int64_t P, P_pad;        // local genes
+    int n_tiles;             // P_pad / TG
+    int64_t gene0;           // global index of local gene 0 (permutation keys use global gene ids)
+};
+
+// ---- streaming passes over Y (k_stream.cu) ------------------------------------------------------------------
+// B_partial[split][N][K] = sum over the split's genes of (M o Y) V^T
+void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, int n_splits,
+                  cudaStream_t st);
+size_t row_b_partial_elems(const Geom& g, int n_splits);
+int row_b_default_splits(const Geom& g, int sm_count);
+// Xty[j][k] = sum_i U[i][k] m_ij y_ij
+void launch_col_xty(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* Ut, double* Xty, int n_blocks,
+                    cudaStream_t st);
+// partial[block][4] = { sse_train, sse_test, sum v^2, sum |v| } over the block's genes; r = y - u.v
+void launch_sse(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const uint32_t* teC, const double* Ut, const double* V,
+                double* partial, int n_blocks, cudaStream_t st);
+int stream_default_blocks(const Geom& g, int sm_count);
+
+// ---- Gram matrices (k_gram.cu) ------------------------------------------------------------------------------
+// Gp[block][KP*KP] partial of V V^T over the block's genes
+void launch_gram_v(const Geom& g, const double* V, double* Gp, int n_blocks, cudaStream_t st);
+// Dp[split][N][KP*KP]: per-row complement Gram sum_{j: m_ij = 0} v_j v_j^T over the split's genes
+void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, double* Dp, int n_splits, cudaStream_t st);
+// fixed-order reductions of the partial buffers:
+//   B[N][K] = sum_s Bp[s] ; G[KP*KP] = sum_b Gp[b] ; D[N][KP*KP] = sum_s Dp[s]
+void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st);
+// UtU[KP*KP] = U^T U   (single block; U is N x KP row-major)
+void launch_gram_u(const Geom& g, const double* U, double* UtU, cudaStream_t st);
+
+// ---- row side (k_rows.cu) -----------------------------------------------------------------------------------
+struct RowDesign {            // one categorical confounder
+    int L;                    // levels
+    const int* level_of_row;  // [N] 0-based
+    const int* rows_sorted;   // [N] rows grouped by level
+    const int* level_start;   // [L+1]
+    double* A;                // [L][KP] row-major factor
+};
+// Gk_c_s[L][KP*KP] = sum_{k in s} (G - D_k)   (masked path; once per iteration per confounder)
+void launch_level_gram(const Geom& g, const RowDesign& d, const double* G, const double* D, double* GL, cudaStream_t st);
+// T[k][:] = B_k - Gk_k (u_k - a_{c,z(k)})   (masked) or  B_k - G (u_k - a)   (dense)
+void launch_row_rhs(const Geom& g, bool masked, const RowDesign& d, const double* B, const double* G, const double* D, const double* U,
+                    double* T, cudaStream_t st);
+// per level: solve (XtX + lambda I) a = sum_{k in s} T_k ; XtX = GL[s] (masked) or n_s G (dense); update A and the rows of U
+void launch_level_solve(const Geom& g, bool masked, const RowDesign& d, const double* G, const double* GL, const double* T, double lambda,
+                        double* U, int* err_flag, cudaStream_t st);
+// continuous covariate q: H = sum_k x_k^2 Gk_k, Tq = sum_k x_k (B_k - Gk_k u_k); cyclic coordinate update / solve; updates w and U
+void launch_continuous(const Geom& g, bool masked, const double* x, double* w /*[KP]*/, const double* B, const double* G, const double* D,
+                       double lambda, double* U, double* scratch, int* err_flag, cudaStream_t st);
+size_t continuous_scratch_elems(const Geom& g);
+// U = sum_c A_c[z_c] + X W ; also writes Ut
+void launch_build_u(const Geom& g, int C, const RowDesign* designs_dev, int Q, const double* X, const double* W, double* U, double* Ut,
+                    cudaStream_t st);
+
+// ---- column side (k_cd.cu) ----------------------------------------------------------------------------------
+struct CdParams {
+    double lambda, alpha;
+    const double* tol;        // device scalar: sub_tol * decay
+    const uint32_t* als_iter; // device scalar
+    uint64_t seed;
+    int perm_mode;
+};
+// per gene: (masked: XtX_j = UtU - sum_{i: m_ij=0} u_i u_i^T) ; alpha == 0 -> ridge solve, else elastic-net CD. Updates V in place.
+void launch_col_solve(const Geom& g, bool masked, const uint32_t* trC, const double* U, const double* UtU, const double* Xty, double* V,
+                      const CdParams& p, unsigned long long* sweeps, int* err_flag, cudaStream_t st);
+// stand-alone batched solver (insider_b200_strong_cd): XtX either shared (KP*KP) or per column [n][KP*KP]
+void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
+                     double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,
+                     cudaStream_t st);
+
+// ---- misc (k_misc.cu) ---------------------------------------------------------------------------------------
+// src: n_genes columns of N mask elements (INSIDER_MASK_* kind) -> dstC[n_genes][Wp] bit-packed
+void launch_pack_mask(const void* src, int kind, int64_t N, int64_t n_genes, int Wp, uint32_t* dstC, cudaStream_t st);
+void launch_transpose_mask(const uint32_t* trC, int64_t N, int64_t P_pad, int Wp, int WPr, uint32_t* trR, cudaStream_t st);
+void launch_count_bits(const uint32_t* m, int64_t n_words, unsigned long long* out, cudaStream_t st);
+struct CheckState {           // device-resident loop state
+    double loss, pre_loss, decay, tol, sub_tol, global_tol;
+    double sse_train, sse_test, v2, v1, row_reg;
+    double train_rmse, test_rmse, delta_loss;
+    double n_train, n_test, np_total;
+    double lambda1, lambda2, alpha;
+    uint32_t als_iter;
+    int converged, diverged, tuning;
+};
+// reduce the SSE partials (fixed order) into state->{sse_train, sse_test, v2, v1}
+void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, cudaStream_t st);
+// row_reg = lambda1 * sum ||A_c||^2 (+ W); then loss, delta, decay ladder, convergence (src/optimize.cpp:381-408)
+void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, void* record_out, cudaStream_t st);
+void launch_bump_iter(CheckState* state, cudaStream_t st);
+
+}  // namespace ib

@@ -1,0 +1,739 @@
+// Host driver of libinsider_b200: context, resident problems, ALS sessions, the C ABI of include/insider_b200.h.
+//
+// The outer loop follows src/optimize.cpp:256-422 step for step (initial evaluation, gram, Gauss-Seidel over
+// confounder blocks, row-factor rebuild, column update, every-10th-iteration evaluation with the decay ladder and
+// the relative-decrease stopping rule) but keeps everything device-resident: the host only launches kernels and,
+// on check iterations, reads back one small record to decide whether to stop.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/insider_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace ib;
+
+namespace {
+
+// ---- minimal NCCL binding (dlopen: the single-GPU path has no NCCL dependency) --------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define SYM(f, n) *(void**)(&f) = dlsym(h, n); if (!f) { err = std::string("missing NCCL symbol ") + n; return false; }
+        SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+        SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+void set_err(char* buf, size_t len, const char* fmt, ...) {
+    if (!buf || len == 0) return;
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, len, fmt, ap); va_end(ap);
+}
+
+struct Err { int code; std::string msg; };
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{INSIDER_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)}; } while (0)
+#define REQUIRE(c, msg) do { if (!(c)) throw Err{INSIDER_ERR_INVALID_ARG, msg}; } while (0)
+
+template <typename T> T* dalloc(size_t n) {
+    T* p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) throw Err{INSIDER_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
+    return p;
+}
+struct DevPool {                       // frees everything it handed out
+    std::vector<void*> ptrs;
+    template <typename T> T* get(size_t n, bool zero = true, cudaStream_t st = 0) {
+        T* p = dalloc<T>(n); ptrs.push_back(p);
+        if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), st);
+        return p;
+    }
+    ~DevPool() { for (void* p : ptrs) cudaFree(p); }
+};
+
+}  // namespace
+
+struct insider_ctx {
+    int device = 0, sm_count = 148, rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    bool profile = false;
+};
+
+struct insider_resident {
+    insider_ctx* ctx = nullptr;
+    int64_t N = 0, P = 0, j0 = 0, Pl = 0, Pl_pad = 0;     // global genes P; this rank owns [j0, j0 + Pl)
+    int C = 0, Q = 0, inc_continuous = 0, has_masks = 0;
+    int ldY = 0, ldT = 0, Wp = 0, WPr = 0;
+    double *Y = nullptr, *X = nullptr;
+    uint32_t *trC = nullptr, *teC = nullptr, *trR = nullptr;
+    std::vector<int> L;
+    std::vector<int*> level_of_row, rows_sorted, level_start;
+    double n_train = 0, n_test = 0;
+    double h2d_bytes = 0;
+    DevPool pool;
+};
+
+struct ProfEntry { std::string name; cudaEvent_t e0, e1; };
+
+struct insider_session {
+    insider_ctx* ctx = nullptr;
+    insider_resident* r = nullptr;
+    insider_options opt{};
+    Geom g{};
+    bool masked = false;
+    int n_factors = 0;
+    std::vector<int> frows;
+    std::vector<size_t> a_off;          // offset (doubles) of factor c inside A_all
+    size_t n_A = 0;
+    double *V = nullptr, *Xty = nullptr, *A_all = nullptr, *U = nullptr, *Ut = nullptr, *UtU = nullptr;
+    double *stats = nullptr, *B = nullptr, *G = nullptr, *D = nullptr;   // stats = [B | G | D] (one all-reduce)
+    size_t stats_elems = 0;
+    double *Bp = nullptr, *Gp = nullptr, *Dp = nullptr, *GL = nullptr, *T = nullptr, *cont_scratch = nullptr, *sse_part = nullptr;
+    double* Vfull = nullptr;            // world > 1: gathered V for the final download
+    std::vector<size_t> gl_off;
+    int rb_splits = 1, gv_blocks = 1, d_splits = 1, stream_blocks = 1;
+    RowDesign* designs_dev = nullptr;
+    std::vector<RowDesign> designs;
+    CheckState* state = nullptr;
+    insider_check* records_dev = nullptr;
+    unsigned long long* sweeps_dev = nullptr;
+    int* err_dev = nullptr;
+    uint32_t max_records = 0, n_records = 0;
+    uint32_t iter = 0;
+    bool done = false;
+    insider_check last{};
+    std::vector<insider_check> records;
+    double loop_ms = 0, h2d = 0, d2h = 0;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<ProfEntry> prof;
+    std::map<std::string, std::pair<double, int64_t>> prof_acc;
+    DevPool pool;
+};
+
+namespace {
+
+struct Launch {                         // counts launches and optionally brackets them with events
+    insider_session* s; const char* name; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Launch(insider_session* s_, const char* n, int count = 1) : s(s_), name(n) {
+        s->launches += count;
+        if (s->ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s->ctx->stream); }
+    }
+    ~Launch() { if (e0) { cudaEventRecord(e1, s->ctx->stream); s->prof.push_back({name, e0, e1}); } }
+};
+
+void drain_profile(insider_session* s) {
+    for (auto& p : s->prof) {
+        cudaEventSynchronize(p.e1);
+        float ms = 0; cudaEventElapsedTime(&ms, p.e0, p.e1);
+        auto& acc = s->prof_acc[p.name]; acc.first += ms; acc.second += 1;
+        cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+    }
+    s->prof.clear();
+}
+
+void nccl_check(int rc, const char* what) {
+    if (rc != 0) throw Err{INSIDER_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error")};
+}
+
+void split_genes(int64_t P, int world, int rank, int64_t& j0, int64_t& n) {
+    // contiguous blocks, multiples of 32 genes so the row-major mask words never straddle ranks
+    const int64_t words = (P + 31) / 32;
+    const int64_t q = words / world, r = words % world;
+    const int64_t w0 = rank * q + std::min<int64_t>(rank, r), w1 = w0 + q + (rank < r ? 1 : 0);
+    j0 = std::min(P, w0 * 32);
+    n = std::min(P, w1 * 32) - j0;
+}
+
+// ---- upload -------------------------------------------------------------------------------------------------
+insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
+    REQUIRE(pb && pb->Y && pb->N > 0 && pb->P > 0, "problem: Y, N, P required");
+    REQUIRE(pb->C >= 0 && (pb->C == 0 || pb->levels), "problem: levels required when C > 0");
+    REQUIRE(pb->inc_continuous == 0 || pb->inc_continuous == 1, "The value of parameter inc_continuous can only be 0 or 1.");
+    REQUIRE(pb->inc_continuous == 0 || (pb->X && pb->Q > 0), "inc_continuous = 1 needs X and Q > 0");
+    REQUIRE(pb->C + pb->inc_continuous > 0, "at least one confounder block is required");
+    REQUIRE(pb->mask_kind >= INSIDER_MASK_NONE && pb->mask_kind <= INSIDER_MASK_DOUBLE, "bad mask_kind");
+    REQUIRE(pb->mask_kind == INSIDER_MASK_NONE || (pb->train && pb->test), "train and test masks required unless mask_kind = NONE");
+    REQUIRE(pb->N < (1 << 30), "N too large");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto* r = new insider_resident();
+    try {
+        r->ctx = ctx; r->N = pb->N; r->P = pb->P; r->C = pb->C; r->Q = pb->inc_continuous ? pb->Q : 0; r->inc_continuous = pb->inc_continuous;
+        r->has_masks = pb->mask_kind != INSIDER_MASK_NONE;
+        split_genes(r->P, ctx->world, ctx->rank, r->j0, r->Pl);
+        r->Pl_pad = std::max<int64_t>(TG, (r->Pl + TG - 1) / TG * TG);
+        const int N = (int)r->N;
+        r->ldY = pitch4(N);
+        r->ldT = pitch4(round_up(N, 8));
+        r->Wp = round_up((r->ldT + 31) / 32, 4);
+        r->WPr = (int)((r->Pl_pad + 31) / 32);
+        // Y: column block [j0, j0+Pl) into pitch ldY, zero padded (+ slack for tile overhang reads)
+        const size_t y_elems = (size_t)r->Pl_pad * r->ldY + 64;
+        r->Y = r->pool.get<double>(y_elems, true, st);
+        if (r->Pl > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(r->Y, (size_t)r->ldY * 8, pb->Y + (size_t)r->j0 * N, (size_t)N * 8, (size_t)N * 8, (size_t)r->Pl,
+                                       cudaMemcpyHostToDevice, st));
+        r->h2d_bytes += (double)r->Pl * N * 8;
+        // design
+        for (int c = 0; c < r->C; ++c) {
+            const int32_t* z = pb->levels + (size_t)c * N;
+            int L = 0;
+            for (int k = 0; k < N; ++k) { REQUIRE(z[k] >= 1, "levels must be 1-based positive integers"); L = std::max(L, (int)z[k]); }
+            std::vector<int> cnt(L + 1, 0), lor(N), sorted(N), start(L + 1, 0);
+            for (int k = 0; k < N; ++k) { lor[k] = z[k] - 1; cnt[lor[k]]++; }
+            for (int l = 0; l < L; ++l) { REQUIRE(cnt[l] > 0, "each confounder column must use every level 1..L_c (reference indexes row level-1)"); start[l + 1] = start[l] + cnt[l]; }
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            for (int k = 0; k < N; ++k) sorted[fill[lor[k]]++] = k;
+            int* d_lor = r->pool.get<int>(N, false); int* d_sorted = r->pool.get<int>(N, false); int* d_start = r->pool.get<int>(L + 1, false);
+            CUDA_TRY(cudaMemcpyAsync(d_lor, lor.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_sorted, sorted.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_start, start.data(), (L + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
+            r->L.push_back(L); r->level_of_row.push_back(d_lor); r->rows_sorted.push_back(d_sorted); r->level_start.push_back(d_start);
+            r->h2d_bytes += (2.0 * N + L + 1) * 4;
+        }
+        if (r->inc_continuous) {
+            r->X = r->pool.get<double>((size_t)N * r->Q, false);
+            CUDA_TRY(cudaMemcpyAsync(r->X, pb->X, (size_t)N * r->Q * 8, cudaMemcpyHostToDevice, st));
+            r->h2d_bytes += (double)N * r->Q * 8;
+        }
+        // masks -> bit planes
+        if (r->has_masks) {
+            const size_t words = (size_t)r->Pl_pad * r->Wp;
+            r->trC = r->pool.get<uint32_t>(words, true, st);
+            r->teC = r->pool.get<uint32_t>(words, true, st);
+            r->trR = r->pool.get<uint32_t>((size_t)N * r->WPr, true, st);
+            const size_t esz = pb->mask_kind == INSIDER_MASK_INT32 ? 4 : pb->mask_kind == INSIDER_MASK_UINT8 ? 1 : 8;
+            const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(r->Pl, (int64_t)((size_t)512 << 20) / (esz * N)));
+            void* tmp = nullptr;
+            CUDA_TRY(cudaMalloc(&tmp, (size_t)chunk * N * esz));
+            try {
+                for (int pass = 0; pass < 2; ++pass) {
+                    const char* src = (const char*)(pass == 0 ? pb->train : pb->test);
+                    uint32_t* dst = pass == 0 ? r->trC : r->teC;
+                    for (int64_t c0 = 0; c0 < r->Pl; c0 += chunk) {
+                        const int64_t n = std::min(chunk, r->Pl - c0);
+                        CUDA_TRY(cudaMemcpyAsync(tmp, src + (size_t)(r->j0 + c0) * N * esz, (size_t)n * N * esz, cudaMemcpyHostToDevice, st));
+                        launch_pack_mask(tmp, pb->mask_kind, N, n, r->Wp, dst + (size_t)c0 * r->Wp, st);
+                        r->h2d_bytes += (double)n * N * esz;
+                    }
+                }
+                launch_transpose_mask(r->trC, N, r->Pl_pad, r->Wp, r->WPr, r->trR, st);
+                unsigned long long* cnt = r->pool.get<unsigned long long>(2, true, st);
+                launch_count_bits(r->trC, (int64_t)words, cnt, st);
+                launch_count_bits(r->teC, (int64_t)words, cnt + 1, st);
+                unsigned long long h[2];
+                CUDA_TRY(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                r->n_train = (double)h[0]; r->n_test = (double)h[1];
+            } catch (...) { cudaFree(tmp); throw; }
+            cudaFree(tmp);
+            if (ctx->world > 1) {
+                double* d2 = r->pool.get<double>(2, false);
+                double hv[2] = {r->n_train, r->n_test};
+                CUDA_TRY(cudaMemcpyAsync(d2, hv, 16, cudaMemcpyHostToDevice, st));
+                nccl_check(g_nccl.AllReduce(d2, d2, 2, NCCL_FLOAT64, NCCL_SUM, ctx->comm, st), "ncclAllReduce(counts)");
+                CUDA_TRY(cudaMemcpyAsync(hv, d2, 16, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                r->n_train = hv[0]; r->n_test = hv[1];
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    } catch (...) { delete r; throw; }
+    return r;
+}
+
+// ---- factor marshalling (host column-major L x K  <->  device row-major L x KP) -----------------------------------
+void upload_factors(insider_session* s, const insider_factors* f) {
+    const int K = s->g.K, KP = s->g.KP;
+    std::vector<double> tmp(s->n_A, 0.0);
+    for (int c = 0; c < s->n_factors; ++c) {
+        const int L = s->frows[c];
+        const double* src = f->factors[c];
+        for (int l = 0; l < L; ++l) for (int k = 0; k < K; ++k) tmp[s->a_off[c] + (size_t)l * KP + k] = src[l + (size_t)k * L];
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->A_all, tmp.data(), s->n_A * 8, cudaMemcpyHostToDevice, s->ctx->stream));
+    const insider_resident* r = s->r;
+    if (r->Pl > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(s->V, (size_t)s->g.ldV * 8, f->column_factor + (size_t)r->j0 * K, (size_t)K * 8, (size_t)K * 8, (size_t)r->Pl,
+                                   cudaMemcpyHostToDevice, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    s->h2d += (double)s->n_A * 8 + (double)r->Pl * K * 8;
+}
+
+void download_factors(insider_session* s, const insider_factors* f) {
+    const int K = s->g.K, KP = s->g.KP;
+    cudaStream_t st = s->ctx->stream;
+    std::vector<double> tmp(s->n_A);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->A_all, s->n_A * 8, cudaMemcpyDeviceToHost, st));
+    const insider_resident* r = s->r;
+    if (s->ctx->world == 1) {
+        CUDA_TRY(cudaMemcpy2DAsync(f->column_factor, (size_t)K * 8, s->V, (size_t)s->g.ldV * 8, (size_t)K * 8, (size_t)r->Pl, cudaMemcpyDeviceToHost, st));
+    } else {
+        // gather every rank's gene block with one broadcast per rank, then one download of the full K x P matrix
+        for (int rk = 0; rk < s->ctx->world; ++rk) {
+            int64_t j0, n; split_genes(r->P, s->ctx->world, rk, j0, n);
+            if (n == 0) continue;
+            nccl_check(g_nccl.Broadcast(s->V, s->Vfull + (size_t)j0 * s->g.ldV, (size_t)n * s->g.ldV, NCCL_FLOAT64, rk, s->ctx->comm, st), "ncclBroadcast(V)");
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(f->column_factor, (size_t)K * 8, s->Vfull, (size_t)s->g.ldV * 8, (size_t)K * 8, (size_t)r->P, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c = 0; c < s->n_factors; ++c) {
+        const int L = s->frows[c];
+        double* dst = f->factors[c];
+        for (int l = 0; l < L; ++l) for (int k = 0; k < K; ++k) dst[l + (size_t)k * L] = tmp[s->a_off[c] + (size_t)l * KP + k];
+    }
+    s->d2h += (double)s->n_A * 8 + (double)(s->ctx->world == 1 ? r->Pl : r->P) * K * 8;
+}
+
+// ---- evaluation (src/optimize.cpp:320-323 and :381-408) -----------------------------------------------------------
+void evaluate(insider_session* s, bool initial) {
+    cudaStream_t st = s->ctx->stream;
+    insider_resident* r = s->r;
+    { Launch l(s, "k_sse"); launch_sse(s->g, s->masked, r->Y, r->trC, r->teC, s->Ut, s->V, s->sse_part, s->stream_blocks, st); }
+    { Launch l(s, "k_sse_reduce"); launch_sse_reduce(s->sse_part, s->stream_blocks, s->state, st); }
+    if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(&s->state->sse_train, &s->state->sse_train, 4, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(sse)");
+    insider_check* rec = s->records_dev + std::min(s->n_records, s->max_records - 1);
+    { Launch l(s, "k_check"); launch_check(s->state, s->A_all, (int64_t)s->n_A, initial ? 1 : 0, rec, st); }
+    struct { insider_check rec; } hostrec;
+    CheckState hs;
+    CUDA_TRY(cudaMemcpyAsync(&hostrec.rec, rec, sizeof(insider_check), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&hs, s->state, sizeof(CheckState), cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, s->err_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    s->d2h += sizeof(insider_check) + sizeof(CheckState) + 4;
+    s->last = hostrec.rec;
+    s->records.push_back(hostrec.rec);
+    s->n_records++;
+    if (s->opt.verbose && s->ctx->rank == 0) {
+        // the reference's console lines (src/optimize.cpp:327-329,387; src/utils.cpp:70-76,95-100)
+        const int it = initial ? 0 : hostrec.rec.iter;
+        printf("insider iter %d: train rmse = %.12g\n", it, hostrec.rec.train_rmse);
+        if (s->opt.tuning == 1) printf("insider iter %d: test rmse = %.12g\n", it, hostrec.rec.test_rmse);
+        printf("total_residual\t%.12g;\nrow_reg_loss:\t%.12g;\ncol_reg_loss:\t%.12g;\nl1_reg_loss:\t%.12g.\n", hostrec.rec.sum_residual / 2,
+               hostrec.rec.row_reg, hostrec.rec.col_reg, hostrec.rec.l1_reg);
+        if (!initial) printf("Delta loss for iter %d:%.12g\n", it, hostrec.rec.delta_loss);
+        fflush(stdout);
+    }
+    if (err) throw Err{INSIDER_ERR_NOT_SPD, "a normal-equation matrix was not positive definite"};
+    if (hs.diverged) throw Err{INSIDER_ERR_DIVERGED, "loss is NaN or Inf"};
+    if (!initial && hs.converged) s->done = true;
+}
+
+// ---- one ALS iteration (src/optimize.cpp:331-378) -------------------------------------------------------------------
+void run_iteration(insider_session* s) {
+    cudaStream_t st = s->ctx->stream;
+    insider_resident* r = s->r;
+    const Geom& g = s->g;
+    const int KK = g.KP * g.KP;
+    // sufficient statistics of the row update: G = V V' (:332), B = (M o Y) V', D_k = complement Grams
+    { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->Gp, s->gv_blocks, st); }
+    { Launch l(s, "k_reduce"); launch_reduce_partials(s->G, s->Gp, KK, s->gv_blocks, st); }
+    { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->rb_splits, st); }
+    { Launch l(s, "k_reduce"); launch_reduce_partials(s->B, s->Bp, (int64_t)g.N * g.KP, s->rb_splits, st); }
+    if (s->masked) {
+        { Launch l(s, "k_row_comp_gram"); launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st); }
+        { Launch l(s, "k_reduce"); launch_reduce_partials(s->D, s->Dp, (int64_t)g.N * KK, s->d_splits, st); }
+    }
+    if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->stats, s->stats, s->stats_elems, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(stats)");
+    // Gauss-Seidel over confounder blocks (:335-362)
+    for (int c = 0; c < r->C; ++c) {
+        const RowDesign& d = s->designs[c];
+        if (s->masked) { Launch l(s, "k_level_gram"); launch_level_gram(g, d, s->G, s->D, s->GL + s->gl_off[c], st); }
+        { Launch l(s, "k_row_rhs"); launch_row_rhs(g, s->masked, d, s->B, s->G, s->D, s->U, s->T, st); }
+        { Launch l(s, "k_level_solve"); launch_level_solve(g, s->masked, d, s->G, s->GL + s->gl_off[c], s->T, s->opt.lambda1, s->U, s->err_dev, st); }
+    }
+    if (r->inc_continuous) {
+        double* W = s->A_all + s->a_off[r->C];
+        for (int q = 0; q < r->Q; ++q) {
+            Launch l(s, "k_continuous", 2);
+            launch_continuous(g, s->masked, r->X + (size_t)q * g.N, W + (size_t)q * g.KP, s->B, s->G, s->D, s->opt.lambda1, s->U, s->cont_scratch, s->err_dev, st);
+        }
+    }
+    // row factor rebuild (:365-373) and column update (:376)
+    { Launch l(s, "k_build_u"); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, st); }
+    { Launch l(s, "k_gram_u", 2); launch_gram_u(g, s->U, s->UtU, st); }
+    { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
+    CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
+    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, r->trC, s->U, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->err_dev, st); }
+}
+
+insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* f, const insider_options* o) {
+    REQUIRE(r && f && o, "null argument");
+    REQUIRE(r->ctx == ctx, "resident problem belongs to another context");
+    REQUIRE(o->tuning == 0 || o->tuning == 1, "Parameter tuning should be either 0 or 1!");
+    if (f->K < 1 || f->K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "latent_dim must be in 1..32"};
+    REQUIRE(f->n_factors == r->C + r->inc_continuous, "n_factors must equal C + inc_continuous");
+    REQUIRE(f->factors && f->factor_rows && f->column_factor, "factor buffers required");
+    REQUIRE(o->tuning == 0 || r->has_masks, "tuning = 1 needs train/test masks");
+    for (int c = 0; c < r->C; ++c) REQUIRE(f->factor_rows[c] == r->L[c], "factor rows must equal the number of levels of the confounder");
+    if (r->inc_continuous) REQUIRE(f->factor_rows[r->C] == r->Q, "continuous factor must be Q x K");
+    if (o->tuning == 1 && r->n_test == 0) throw Err{INSIDER_ERR_EMPTY_TEST_SET, "tuning = 1 but the test indicator is empty"};
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto* s = new insider_session();
+    try {
+        s->ctx = ctx; s->r = r; s->opt = *o;
+        if (s->opt.check_every == 0) s->opt.check_every = 10;
+        if (s->opt.perm_mode == 0) s->opt.perm_mode = INSIDER_PERM_COUNTER;
+        REQUIRE(s->opt.perm_mode == INSIDER_PERM_COUNTER || s->opt.perm_mode == INSIDER_PERM_IDENTITY, "bad perm_mode");
+        s->masked = o->tuning == 1;
+        Geom& g = s->g;
+        g.N = (int)r->N; g.K = f->K; g.KP = round_up(f->K, 8); g.NT = g.KP / 8;
+        g.ldY = r->ldY; g.ldV = pitch4(g.KP); g.ldT = r->ldT; g.Wp = r->Wp; g.WPr = r->WPr;
+        g.P = r->Pl; g.P_pad = r->Pl_pad; g.n_tiles = (int)(r->Pl_pad / TG); g.gene0 = r->j0;
+        s->n_factors = f->n_factors;
+        size_t off = 0;
+        for (int c = 0; c < f->n_factors; ++c) { s->frows.push_back(f->factor_rows[c]); s->a_off.push_back(off); off += (size_t)f->factor_rows[c] * g.KP; }
+        s->n_A = off;
+        const int KK = g.KP * g.KP;
+        s->V = s->pool.get<double>((size_t)g.P_pad * g.ldV + 64, true, st);
+        s->Xty = s->pool.get<double>((size_t)g.P_pad * g.ldV + 64, true, st);
+        s->A_all = s->pool.get<double>(s->n_A, true, st);
+        s->U = s->pool.get<double>((size_t)g.N * g.KP, true, st);
+        s->Ut = s->pool.get<double>((size_t)g.KP * g.ldT + 64, true, st);
+        s->UtU = s->pool.get<double>((size_t)KK * (1 + (g.N + 255) / 256), true, st);
+        s->stats_elems = (size_t)g.N * g.KP + KK + (s->masked ? (size_t)g.N * KK : 0);
+        s->stats = s->pool.get<double>(s->stats_elems, true, st);
+        s->B = s->stats; s->G = s->B + (size_t)g.N * g.KP; s->D = s->masked ? s->G + KK : nullptr;
+        s->rb_splits = row_b_default_splits(g, ctx->sm_count);
+        s->Bp = s->pool.get<double>(row_b_partial_elems(g, s->rb_splits), true, st);
+        s->gv_blocks = std::max(1, std::min(ctx->sm_count, (int)(g.P_pad / 64)));
+        s->Gp = s->pool.get<double>((size_t)s->gv_blocks * KK, true, st);
+        s->stream_blocks = stream_default_blocks(g, ctx->sm_count);
+        s->sse_part = s->pool.get<double>((size_t)s->stream_blocks * 4, true, st);
+        s->T = s->pool.get<double>((size_t)g.N * g.KP, true, st);
+        if (s->masked) {
+            s->d_splits = std::max(1, std::min(16, (ctx->sm_count * 16 + g.N - 1) / g.N));
+            s->d_splits = std::min(s->d_splits, std::max(1, g.WPr));
+            s->Dp = s->pool.get<double>((size_t)s->d_splits * g.N * KK, true, st);
+            size_t go = 0;
+            for (int c = 0; c < r->C; ++c) { s->gl_off.push_back(go); go += (size_t)r->L[c] * KK; }
+            s->GL = s->pool.get<double>(go, true, st);
+        } else {
+            for (int c = 0; c < r->C; ++c) s->gl_off.push_back(0);
+            s->GL = s->pool.get<double>(1, true, st);
+        }
+        if (r->inc_continuous) s->cont_scratch = s->pool.get<double>(continuous_scratch_elems(g), true, st);
+        if (ctx->world > 1) s->Vfull = s->pool.get<double>((size_t)r->P * g.ldV, true, st);
+        for (int c = 0; c < r->C; ++c) s->designs.push_back(RowDesign{r->L[c], r->level_of_row[c], r->rows_sorted[c], r->level_start[c], s->A_all + s->a_off[c]});
+        s->designs_dev = s->pool.get<RowDesign>(std::max(1, r->C), true, st);
+        if (r->C) CUDA_TRY(cudaMemcpyAsync(s->designs_dev, s->designs.data(), r->C * sizeof(RowDesign), cudaMemcpyHostToDevice, st));
+        s->state = s->pool.get<CheckState>(1, true, st);
+        CheckState hs{};
+        hs.sub_tol = o->sub_tol; hs.global_tol = o->global_tol; hs.tol = o->sub_tol; hs.decay = 1.0;
+        hs.n_train = r->n_train; hs.n_test = r->n_test; hs.np_total = (double)r->N * (double)r->P;
+        hs.lambda1 = o->lambda1; hs.lambda2 = o->lambda2; hs.alpha = o->alpha; hs.tuning = o->tuning; hs.als_iter = 0;
+        CUDA_TRY(cudaMemcpyAsync(s->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+        s->max_records = (uint32_t)std::min<uint64_t>((uint64_t)o->max_iter / s->opt.check_every + 3, 1u << 20);
+        s->records_dev = s->pool.get<insider_check>(s->max_records, true, st);
+        s->sweeps_dev = s->pool.get<unsigned long long>(1, true, st);
+        s->err_dev = s->pool.get<int>(1, true, st);
+        CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
+        upload_factors(s, f);
+        // initial row factor and evaluation (:286-289, :320-323)
+        { Launch l(s, "k_build_u"); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, st); }
+        evaluate(s, true);
+    } catch (...) { if (s->ev0) cudaEventDestroy(s->ev0); if (s->ev1) cudaEventDestroy(s->ev1); delete s; throw; }
+    return s;
+}
+
+void do_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms) {
+    CUDA_TRY(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    CUDA_TRY(cudaEventRecord(s->ev0, st));
+    uint32_t ran = 0;
+    while (!s->done && ran < n_iters) {
+        if (s->iter > s->opt.max_iter) { s->done = true; break; }                  // while(iter <= max_iter)  :325
+        run_iteration(s);
+        if (s->iter % s->opt.check_every == 0) evaluate(s, false);                 // :381
+        if (s->done) break;                                                        // :405-407 (iter not incremented on break)
+        { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
+        s->iter++; ran++;                                                          // :409
+        if (s->iter > s->opt.max_iter) s->done = true;
+    }
+    CUDA_TRY(cudaEventRecord(s->ev1, st));
+    CUDA_TRY(cudaEventSynchronize(s->ev1));
+    CUDA_TRY(cudaGetLastError());
+    float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, s->ev0, s->ev1));
+    s->loop_ms += t;
+    if (ms) *ms = t;
+    if (done) *done = s->done ? 1 : 0;
+    if (s->ctx->profile) drain_profile(s);
+}
+
+void fill_result(insider_session* s, insider_result* res) {
+    if (!res) return;
+    unsigned long long sw = 0; int err = 0;
+    CUDA_TRY(cudaMemcpy(&sw, s->sweeps_dev, 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));
+    res->train_rmse = s->last.train_rmse; res->test_rmse = s->last.test_rmse; res->loss = s->last.loss;
+    res->iters_run = s->iter;
+    res->n_checks = (uint32_t)std::min<size_t>(s->records.size(), res->checks ? res->max_checks : s->records.size());
+    if (res->checks) for (uint32_t i = 0; i < res->n_checks; ++i) res->checks[i] = s->records[i];
+    res->cd_sweeps = (int64_t)sw; res->loop_ms = s->loop_ms; res->h2d_bytes = s->h2d; res->d2h_bytes = s->d2h; res->kernel_launches = s->launches;
+    if (err) throw Err{INSIDER_ERR_NOT_SPD, "a normal-equation matrix was not positive definite"};
+}
+
+void destroy_session(insider_session* s) {
+    if (!s) return;
+    for (auto& p : s->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+template <typename F> int guarded(char* errbuf, size_t errlen, F&& fn) {
+    try { fn(); return INSIDER_OK; }
+    catch (const Err& e) { set_err(errbuf, errlen, "%s", e.msg.c_str()); cudaGetLastError(); return e.code; }
+    catch (const std::bad_alloc&) { set_err(errbuf, errlen, "host out of memory"); return INSIDER_ERR_NOMEM; }
+    catch (const std::exception& e) { set_err(errbuf, errlen, "%s", e.what()); return INSIDER_ERR_INVALID_ARG; }
+    catch (...) { set_err(errbuf, errlen, "unknown error"); return INSIDER_ERR_INVALID_ARG; }
+}
+
+int create_ctx(insider_ctx** out, int device, int rank, int world, const void* id, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(out, "null out pointer");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw Err{INSIDER_ERR_CUDA, "no CUDA device available (libinsider_b200 has no CPU fallback)"};
+        REQUIRE(device >= 0 && device < n, "bad device index");
+        cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw Err{INSIDER_ERR_CUDA, "libinsider_b200 is built for sm_100a (B200) only"};
+        CUDA_TRY(cudaSetDevice(device));
+        auto* c = new insider_ctx();
+        c->device = device; c->sm_count = prop.multiProcessorCount; c->rank = rank; c->world = world;
+        try {
+            CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            if (world > 1) {
+                std::string err;
+                if (!g_nccl.load(err)) throw Err{INSIDER_ERR_NCCL, err};
+                ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
+                nccl_check(g_nccl.CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
+            }
+        } catch (...) { if (c->stream) cudaStreamDestroy(c->stream); delete c; throw; }
+        *out = c;
+    });
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int insider_b200_version(void) { return INSIDER_B200_VERSION; }
+
+void insider_b200_default_options(insider_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->lambda1 = 1.0; o->lambda2 = 1.0; o->alpha = 0.1; o->tuning = 1;             // src/optimize.cpp:257
+    o->global_tol = 1e-10; o->sub_tol = 1e-5; o->max_iter = 10000; o->check_every = 10;
+    o->perm_mode = INSIDER_PERM_COUNTER; o->seed = 0; o->verbose = 0; o->use_graph = 0;
+}
+
+int insider_b200_ctx_create(insider_ctx** out, int device, char* errbuf, size_t errlen) { return create_ctx(out, device, 0, 1, nullptr, errbuf, errlen); }
+
+int insider_b200_nccl_unique_id(void* out128, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(out128, "null buffer");
+        std::string err;
+        if (!g_nccl.load(err)) throw Err{INSIDER_ERR_NCCL, err};
+        ncclUniqueId uid; nccl_check(g_nccl.GetUniqueId(&uid), "ncclGetUniqueId");
+        memcpy(out128, &uid, sizeof(uid));
+    });
+}
+
+int insider_b200_ctx_create_dist(insider_ctx** out, int device, int rank, int world, const void* nccl_id128, char* errbuf, size_t errlen) {
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_id128)) { set_err(errbuf, errlen, "bad rank/world/nccl id"); return INSIDER_ERR_INVALID_ARG; }
+    return create_ctx(out, device, rank, world, nccl_id128, errbuf, errlen);
+}
+
+void insider_b200_ctx_destroy(insider_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* insider_b200_ctx_stream(insider_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void insider_b200_set_profile(insider_ctx* c, int on) { if (c) c->profile = on != 0; }
+
+int insider_b200_upload(insider_ctx* ctx, const insider_problem* prob, insider_resident** out, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] { REQUIRE(ctx && out, "null argument"); *out = do_upload(ctx, prob); });
+}
+void insider_b200_release(insider_resident* r) { if (r) { cudaSetDevice(r->ctx->device); delete r; } }
+
+int insider_b200_als_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* fac, const insider_options* opt, insider_session** out,
+                           char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] { REQUIRE(ctx && out, "null argument"); *out = do_begin(ctx, r, fac, opt); });
+}
+int insider_b200_als_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] { REQUIRE(s, "null session"); do_step(s, n_iters, done, ms); });
+}
+int insider_b200_als_read(insider_session* s, const insider_factors* fac, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] { REQUIRE(s && fac, "null argument"); download_factors(s, fac); });
+}
+int insider_b200_als_end(insider_session* s, const insider_factors* fac, insider_result* res, char* errbuf, size_t errlen) {
+    int rc = guarded(errbuf, errlen, [&] {
+        REQUIRE(s, "null session");
+        if (fac) download_factors(s, fac);
+        fill_result(s, res);
+    });
+    destroy_session(s);
+    return rc;
+}
+int insider_b200_als_profile(insider_session* s, char* names, size_t names_len, double* ms, int64_t* calls, int max_entries) {
+    if (!s) return 0;
+    std::string joined; int n = 0;
+    for (auto& kv : s->prof_acc) {
+        if (n >= max_entries) break;
+        if (n) joined += "\n";
+        joined += kv.first;
+        if (ms) ms[n] = kv.second.first;
+        if (calls) calls[n] = kv.second.second;
+        ++n;
+    }
+    if (names && names_len) { strncpy(names, joined.c_str(), names_len - 1); names[names_len - 1] = 0; }
+    return n;
+}
+
+int insider_b200_optimize_resident(insider_ctx* ctx, insider_resident* r, const insider_factors* fac, const insider_options* opt, insider_result* res,
+                                   char* errbuf, size_t errlen) {
+    insider_session* s = nullptr;
+    int rc = insider_b200_als_begin(ctx, r, fac, opt, &s, errbuf, errlen);
+    if (rc) return rc;
+    int32_t done = 0;
+    while (!done) {
+        rc = insider_b200_als_step(s, 1000, &done, nullptr, errbuf, errlen);
+        if (rc) { destroy_session(s); return rc; }
+    }
+    return insider_b200_als_end(s, fac, res, errbuf, errlen);
+}
+
+int insider_b200_optimize(insider_ctx* ctx, const insider_problem* prob, const insider_factors* fac, const insider_options* opt, insider_result* res,
+                          char* errbuf, size_t errlen) {
+    insider_resident* r = nullptr;
+    int rc = insider_b200_upload(ctx, prob, &r, errbuf, errlen);
+    if (rc) return rc;
+    const double up = r->h2d_bytes;
+    rc = insider_b200_optimize_resident(ctx, r, fac, opt, res, errbuf, errlen);
+    if (rc == INSIDER_OK && res) res->h2d_bytes += up;
+    insider_b200_release(r);
+    return rc;
+}
+
+int insider_b200_tune_batch(insider_ctx* ctx, insider_resident* r, int32_t n_points, const insider_factors* fac, const insider_options* opt,
+                            insider_result* res, char* errbuf, size_t errlen) {
+    if (!fac || !opt || !res || n_points < 0) { set_err(errbuf, errlen, "null argument"); return INSIDER_ERR_INVALID_ARG; }
+    for (int i = 0; i < n_points; ++i) {
+        int rc = insider_b200_optimize_resident(ctx, r, &fac[i], &opt[i], &res[i], errbuf, errlen);
+        if (rc) return rc;
+    }
+    return INSIDER_OK;
+}
+
+int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const double* XtX, int32_t shared_gram, const double* Xty, const double* wstart,
+                           double lambda, double alpha, double tol, int32_t perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta,
+                           int32_t* sweeps, char* errbuf, size_t errlen) {
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(ctx && XtX && Xty && wstart && beta && n_cols >= 0, "null argument");
+        if (K < 1 || K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "K must be in 1..32"};
+        if (perm_mode == 0) perm_mode = INSIDER_PERM_COUNTER;
+        if (n_cols == 0) return;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        DevPool pool;
+        const size_t gsz = (size_t)K * K * (shared_gram ? 1 : n_cols);
+        double* dG = pool.get<double>(gsz, false); double* dx = pool.get<double>((size_t)K * n_cols, false);
+        double* dw = pool.get<double>((size_t)K * n_cols, false); double* db = pool.get<double>((size_t)K * n_cols, true, st);
+        int* dsw = pool.get<int>(n_cols, true, st);
+        CUDA_TRY(cudaMemcpyAsync(dG, XtX, gsz * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dx, Xty, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dw, wstart, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
+        launch_cd_batch(K, n_cols, dG, shared_gram != 0, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, st);
+        CUDA_TRY(cudaMemcpyAsync(beta, db, (size_t)K * n_cols * 8, cudaMemcpyDeviceToHost, st));
+        if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, (size_t)n_cols * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    });
+}
+
+int insider_b200_fit_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t K, const double* residual, int32_t mask_kind, const void* train,
+                                 double* interactions, int32_t n_levels, const int32_t* indicator, const double* column_factor, int32_t tuning,
+                                 char* errbuf, size_t errlen) {
+    // per-level normal equations without ridge on a caller-supplied residual: the row update of one confounder with
+    // lambda = 0 and a zero row factor (then T_k = B_k and XtX_s = sum Gk_k)  — src/fit_interaction.cpp:37-54 / :59-82
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(ctx && residual && interactions && indicator && column_factor, "null argument");
+        REQUIRE(tuning == 0 || tuning == 1, "Parameter tuning should be either 0 or 1!");
+        REQUIRE(ctx->world == 1, "fit_interaction runs on a single-GPU context");
+        insider_problem pb{};
+        pb.N = N; pb.P = P; pb.C = 1; pb.Q = 0; pb.inc_continuous = 0; pb.Y = residual; pb.levels = indicator;
+        pb.mask_kind = tuning == 1 ? mask_kind : INSIDER_MASK_NONE; pb.train = train; pb.test = train;
+        std::unique_ptr<insider_resident, void (*)(insider_resident*)> r(do_upload(ctx, &pb), insider_b200_release);
+        REQUIRE(r->L[0] == n_levels, "n_levels must equal the number of interaction levels");
+        std::vector<double> A0((size_t)n_levels * K, 0.0), V((size_t)K * P);
+        memcpy(V.data(), column_factor, V.size() * 8);
+        double* fp[1] = {A0.data()}; int32_t rows[1] = {n_levels};
+        insider_factors f{K, 1, fp, rows, V.data()};
+        insider_options o; insider_b200_default_options(&o);
+        o.tuning = tuning; o.lambda1 = 0.0; o.max_iter = 0;
+        insider_session* s = do_begin(ctx, r.get(), &f, &o);
+        try {
+            cudaStream_t st = ctx->stream;
+            const Geom& g = s->g; const int KK = g.KP * g.KP;
+            launch_gram_v(g, s->V, s->Gp, s->gv_blocks, st);
+            launch_reduce_partials(s->G, s->Gp, KK, s->gv_blocks, st);
+            launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->rb_splits, st);
+            launch_reduce_partials(s->B, s->Bp, (int64_t)g.N * g.KP, s->rb_splits, st);
+            if (s->masked) {
+                launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st);
+                launch_reduce_partials(s->D, s->Dp, (int64_t)g.N * KK, s->d_splits, st);
+                launch_level_gram(g, s->designs[0], s->G, s->D, s->GL, st);
+            }
+            launch_row_rhs(g, s->masked, s->designs[0], s->B, s->G, s->D, s->U, s->T, st);
+            launch_level_solve(g, s->masked, s->designs[0], s->G, s->GL, s->T, 0.0, s->U, s->err_dev, st);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            download_factors(s, &f);
+            int err = 0; CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));
+            if (err) throw Err{INSIDER_ERR_NOT_SPD, "interaction normal equations not positive definite"};
+        } catch (...) { destroy_session(s); throw; }
+        destroy_session(s);
+        memcpy(interactions, A0.data(), A0.size() * 8);
+    });
+}
+
+}  // extern "C"

@@ -28,7 +28,7 @@ __host__ __device__ inline uint64_t perm_key(uint64_t seed, uint32_t als_iter, u
            mix64(gene * 0xD1B54A32D192ED03ull + (uint64_t)draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
 }
 __host__ __device__ inline uint32_t perm_value(uint64_t key, int pos) {
-    return (uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(pos + 1)) >> 33);
+    return (uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(pos + 1)) >> 38);   // 26 bits: (value << 5 | coordinate) fits a u32 sort key
 }
 
 #ifdef __CUDACC__

@@ -80,146 +80,169 @@ __device__ double warp_chol_subst(const double* S, int ld, int K, int lane, doub
 
 // ---------------------------------------------------------------------------------------------------------------
 // elastic-net coordinate descent for the 4 genes of a warp (one 8-lane group each).
-//   Xs: this group's symmetric K x K matrix in shared memory (leading dimension ld); ord_s: 32 bytes of scratch per group
+//   Xs : this group's symmetric KP x KP matrix in shared memory (leading dimension ld, zero padded)
+//   sh : per-group scratch, 5*KP doubles  [beta | q | d | den | 1/den] indexed by coordinate
+//   ord_s : 32 bytes per group
+// Data lives in two layouts. "Coordinate layout": lane li, slot s holds coordinate c = s*8 + li. "Position layout":
+// lane li, slot s holds the coordinate visited at step i = s*8 + li of the current sweep (inactive ones behind the
+// n_inc active ones). Each sweep re-labels registers into position layout through `sh`, so the unrolled step loop has a
+// compile-time owner lane and slot: no dynamic register indexing anywhere in the sweep.
 template <int SL>
 __device__ void group_cd(const double* Xs, int ld, int K, int li, bool gvalid, const double (&xty)[SL], double (&beta)[SL], double lambda,
-                         double alpha, double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene,
+                         double alpha, double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene, double* sh,
                          unsigned char* ord_s, int& sweeps_out) {
+    constexpr int KP = SL * LPG;
     const int lane = threadIdx.x & 31;
     const int grp_shift = (lane >> 3) << 3;
     const double la = lambda * alpha, l2 = lambda * (1.0 - alpha);
-    double d[SL], q[SL], rden[SL], den[SL];
-    bool act[SL];
-    double mx = 0.0;
+    double* Bc = sh; double* Qc = sh + KP; double* Dc = sh + 2 * KP; double* DENc = sh + 3 * KP; double* RDc = sh + 4 * KP;
+    uint32_t inc = 0;                                                       // active coordinates (group-uniform)
+    {
+        double mx = 0.0;
 #pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int c = s * LPG + li;
-        d[s] = (c < K) ? Xs[c * ld + c] : 0.0;
-        mx = fmax(mx, (c < K) ? fabs(xty[s]) : 0.0);
-    }
-    mx = grp_max(mx);
-    const double thr = alpha * (2.0 * lambda - mx);                        // coordinate_descent.cpp:74
+        for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; mx = fmax(mx, (c < K) ? fabs(xty[s]) : 0.0); }
+        mx = grp_max(mx);
+        const double thr = alpha * (2.0 * lambda - mx);                    // coordinate_descent.cpp:74
+        double q[SL];
 #pragma unroll
-    for (int s = 0; s < SL; ++s) {
-        const int c = s * LPG + li;
-        act[s] = (c < K) && !(fabs(xty[s]) < thr);
-        if (!act[s]) beta[s] = 0.0;                                        // :75-78
-        q[s] = (c < K) ? xty[s] : 0.0;
-        den[s] = d[s] + l2;
-        rden[s] = 1.0 / den[s];
-    }
-    // q = X'y - X'X beta
-#pragma unroll
-    for (int ms = 0; ms < SL; ++ms)
-        for (int ml = 0; ml < LPG; ++ml) {
-            const int m = ms * LPG + ml;
-            const double bm = __shfl_sync(FULL, beta[ms], ml, LPG);
-            if (m < K) {
-#pragma unroll
-                for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) q[s] = fma(-Xs[m * ld + c], bm, q[s]); }
-            }
+        for (int s = 0; s < SL; ++s) {
+            const int c = s * LPG + li;
+            const bool a = (c < K) && !(fabs(xty[s]) < thr);
+            if (!a) beta[s] = 0.0;                                         // :75-78
+            const uint32_t b = __ballot_sync(FULL, a);
+            inc |= ((b >> grp_shift) & 0xffu) << (LPG * s);
+            q[s] = (c < K) ? xty[s] : 0.0;
         }
+        // q = X'y - X'X beta
+#pragma unroll
+        for (int ms = 0; ms < SL; ++ms)
+            for (int ml = 0; ml < LPG; ++ml) {
+                const int m = ms * LPG + ml;
+                const double bm = __shfl_sync(FULL, beta[ms], ml, LPG);
+                if (m < K && bm != 0.0) {
+#pragma unroll
+                    for (int s = 0; s < SL; ++s) q[s] = fma(-Xs[m * ld + s * LPG + li], bm, q[s]);
+                }
+            }
+#pragma unroll
+        for (int s = 0; s < SL; ++s) {
+            const int c = s * LPG + li;
+            const double d = Xs[c * ld + c], den = d + l2;
+            Bc[c] = beta[s]; Qc[c] = q[s]; Dc[c] = d; DENc[c] = den; RDc[c] = 1.0 / den;
+        }
+    }
+    const uint32_t valid_mask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
+    int n_inc = __popc(inc);
     bool done = !gvalid;
     uint32_t draw = 0;
     int sweeps = 0;
-    uint32_t inc = 0;
-    int n_inc = 0;
-    auto rebuild_inc = [&]() {
-        inc = 0;
-#pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            const uint32_t b = __ballot_sync(FULL, act[s]);
-            inc |= ((b >> grp_shift) & 0xffu) << (LPG * s);
-        }
-        n_inc = __popc(inc);
-    };
-    rebuild_inc();
     while (true) {
-        // ---- visiting order of the active coordinates (coordinate_descent.cpp:89)
-        int rank[SL];
-        if (perm_mode == 1) {
-            const uint64_t key = perm_key(seed, als_iter, gene, draw);
-            uint32_t v[SL];
+        // ---- visiting order (coordinate_descent.cpp:89): rank of every coordinate, in coordinate layout
+        int pos[SL];
+        {
+            uint32_t key[SL];
+            const uint64_t pk = perm_key(seed, als_iter, gene, draw);
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 const int c = s * LPG + li;
-                v[s] = perm_value(key, __popc(inc & ((1u << c) - 1u)));
-                rank[s] = 0;
+                const uint32_t below = (1u << c) - 1u;
+                const int p_act = __popc(inc & below);
+                key[s] = (perm_mode == 1) ? ((perm_value(pk, p_act) << 5) | (uint32_t)c) : (uint32_t)c;
+                // inactive coordinates keep ascending order behind the active ones; padding (c >= K) stays last
+                pos[s] = (c < K) ? n_inc + __popc(~inc & valid_mask & below) : c;
             }
+            int rank[SL];
+#pragma unroll
+            for (int s = 0; s < SL; ++s) rank[s] = 0;
 #pragma unroll
             for (int ms = 0; ms < SL; ++ms)
+#pragma unroll
                 for (int ml = 0; ml < LPG; ++ml) {
                     const int m = ms * LPG + ml;
-                    const uint32_t vm = __shfl_sync(FULL, v[ms], ml, LPG);
-                    if ((inc >> m) & 1u) {
+                    const uint32_t km = __shfl_sync(FULL, key[ms], ml, LPG);
+                    const uint32_t am = (inc >> m) & 1u;
 #pragma unroll
-                        for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; rank[s] += (vm < v[s]) || (vm == v[s] && m < c); }
-                    }
+                    for (int s = 0; s < SL; ++s) rank[s] += (int)(am & (uint32_t)(km < key[s]));
                 }
-        } else {
 #pragma unroll
-            for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; rank[s] = __popc(inc & ((1u << c) - 1u)); }
+            for (int s = 0; s < SL; ++s) if ((inc >> (s * LPG + li)) & 1u) pos[s] = rank[s];
         }
         ++draw;
         __syncwarp();
 #pragma unroll
-        for (int s = 0; s < SL; ++s) if (act[s]) ord_s[rank[s]] = (unsigned char)(s * LPG + li);
+        for (int s = 0; s < SL; ++s) ord_s[pos[s]] = (unsigned char)(s * LPG + li);
         __syncwarp();
-        // ---- one sweep
+        // ---- gather into position layout
+        int cd[SL];
+        double b[SL], q[SL], d[SL], den[SL], rd[SL];
+#pragma unroll
+        for (int s = 0; s < SL; ++s) {
+            const int c = ord_s[s * LPG + li];
+            cd[s] = c; b[s] = Bc[c]; q[s] = Qc[c]; d[s] = Dc[c]; den[s] = DENc[c]; rd[s] = RDc[c];
+        }
         int nmax = done ? 0 : n_inc;
         nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 8));
         nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 16));
+        const int n_on = done ? 0 : n_inc;
         double dl = 0.0;
-        for (int i = 0; i < nmax; ++i) {
-            const bool on = !done && i < n_inc;
-            const int k = on ? (int)ord_s[i] : 0;
-            const int ks = k >> 3, kl = k & 7;
-            const double bo = sel<SL>(beta, ks), dk = sel<SL>(d, ks), qk = sel<SL>(q, ks);
+        // ---- one sweep; step i is owned by lane (i & 7), slot (i >> 3)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            if (i >= nmax) break;
+            constexpr int dummy = 0; (void)dummy;
+            const int si = i >> 3, ow = i & 7;
+            const double bo = b[si], qk = q[si], dk = d[si];
             const double up = fma(bo, dk, qk);                             // :94
             const double t1 = fabs(up) - la;
             double nb = 0.0;
             if (t1 > 0.0) {                                                // :99-104
-                const double num = copysign(t1, up), dn = sel<SL>(den, ks), rd = sel<SL>(rden, ks);
-                nb = num * rd;                                             // correctly rounded num / dn (Markstein)
-                const double e = fma(-dn, nb, num);
-                nb = fma(e, rd, nb);
+                const double num = copysign(t1, up);
+                nb = num * rd[si];                                         // correctly rounded num / den (Markstein)
+                nb = fma(fma(-den[si], nb, num), rd[si], nb);
             }
             double dlt = nb - bo;
-            if (!on) dlt = 0.0;
-            const double dkk = __shfl_sync(FULL, dlt, kl, LPG);
+            if (i >= n_on) dlt = 0.0;
+            const double dkk = __shfl_sync(FULL, dlt, ow, LPG);
+            const int kk = __shfl_sync(FULL, cd[si], ow, LPG);
             if (dkk != 0.0) {                                              // :106-109
-                if (li == kl) {
+                if (li == ow) {
                     const double s3 = fma(0.5 * l2, nb + bo, fma(0.5 * dk, dlt, -qk));
                     dl = fma(dlt, s3, dl);
                     dl = fma(la, fabs(nb) - fabs(bo), dl);
-#pragma unroll
-                    for (int s = 0; s < SL; ++s) if (s == ks) beta[s] = nb;
+                    b[si] = nb;
                 }
+                const double* xr = Xs + kk * ld;
 #pragma unroll
-                for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) q[s] = fma(-dkk, Xs[k * ld + c], q[s]); }
+                for (int s = 0; s < SL; ++s) q[s] = fma(-dkk, xr[cd[s]], q[s]);
             }
         }
+        // ---- scatter back to coordinate layout
+#pragma unroll
+        for (int s = 0; s < SL; ++s) { Bc[cd[s]] = b[s]; Qc[cd[s]] = q[s]; }
         const double delta = grp_sum(dl);
-        // inner do-while ends (:114) -> KKT check on the excluded set (:118-124); ballots are executed by every lane
+        // inner do-while ends (:114) -> KKT check on the excluded set (:118-124)
         const bool inner_end = !done && (!(fabs(delta) > tol) || sweeps + 1 >= MAX_SWEEPS);
-        bool viol = false;
+        uint32_t vmask = 0;
         if (inner_end) {
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
-                const int c = s * LPG + li;
-                const bool vs = (c < K) && !act[s] && (fabs(q[s]) > la);
-                if (vs) act[s] = true;
-                viol |= vs;
+                const int i = s * LPG + li;
+                if (i >= n_inc && cd[s] < K && fabs(q[s]) > la) vmask |= 1u << cd[s];
             }
         }
-        const uint32_t vb = __ballot_sync(FULL, viol);
+        vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
         if (!done) {
             ++sweeps;
-            if (inner_end && ((((vb >> grp_shift) & 0xffu) == 0u) || sweeps >= MAX_SWEEPS)) done = true;
+            if (inner_end) {
+                if (vmask == 0u || sweeps >= MAX_SWEEPS) done = true;
+                else { inc |= vmask; n_inc = __popc(inc); }
+            }
         }
-        rebuild_inc();
         if (__all_sync(FULL, done)) break;
     }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < SL; ++s) beta[s] = Bc[s * LPG + li];
     sweeps_out = gvalid ? sweeps : 0;
 }
 
@@ -296,7 +319,8 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_col_solve(SolveArgs a) {
     double* Xall = reinterpret_cast<double*>(smem_raw);
     // MASKED: one matrix per gene [CD_WARPS][GPW][KP*XLD]; dense: one shared matrix (+ one factor for ridge)
     const int n_mats = MASKED ? CD_WARPS * GPW : 1;
-    unsigned char* ord_all = reinterpret_cast<unsigned char*>(Xall + (size_t)n_mats * KP * XLD);
+    double* sh_all = Xall + (size_t)n_mats * KP * XLD;                    // [CD_WARPS*GPW][5*KP]
+    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)CD_WARPS * GPW * 5 * KP);
     const int64_t j0 = ((int64_t)blockIdx.x * CD_WARPS + warp) * GPW;
     const double tol = *a.tol;
     const uint32_t als_iter = *a.als_iter;
@@ -352,7 +376,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_col_solve(SolveArgs a) {
     const double* Xs = MASKED ? Xw + (size_t)grp * KP * XLD : Xall;
     int sweeps = 0;
     group_cd<SL>(Xs, XLD, a.K, li, gvalid, xty, beta, a.lambda, a.alpha, tol, a.perm_mode, a.seed, als_iter, (uint64_t)(a.gene0 + j),
-                 ord_all + (warp * GPW + grp) * 32, sweeps);
+                 sh_all + (size_t)(warp * GPW + grp) * 5 * KP, ord_all + (warp * GPW + grp) * 32, sweeps);
     if (gvalid) {
 #pragma unroll
         for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < a.K) a.V[j * a.ldV + c] = beta[s]; }
@@ -375,7 +399,8 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_batch(BatchArgs a) {
     constexpr int XLD = KP + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, li = lane & 7;
     double* Xall = reinterpret_cast<double*>(smem_raw);
-    unsigned char* ord_all = reinterpret_cast<unsigned char*>(Xall + (size_t)CD_WARPS * GPW * KP * XLD);
+    double* sh_all = Xall + (size_t)CD_WARPS * GPW * KP * XLD;
+    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)CD_WARPS * GPW * 5 * KP);
     const int64_t j0 = ((int64_t)blockIdx.x * CD_WARPS + warp) * GPW;
     double* Xw = Xall + (size_t)warp * GPW * KP * XLD;
     for (int gi = 0; gi < GPW; ++gi) {
@@ -399,7 +424,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_batch(BatchArgs a) {
     }
     int sweeps = 0;
     group_cd<SL>(Xw + (size_t)grp * KP * XLD, XLD, a.K, li, gvalid, xty, beta, a.lambda, a.alpha, a.tol, a.perm_mode, a.seed, a.als_iter,
-                 a.gene0 + (uint64_t)j, ord_all + (warp * GPW + grp) * 32, sweeps);
+                 a.gene0 + (uint64_t)j, sh_all + (size_t)(warp * GPW + grp) * 5 * KP, ord_all + (warp * GPW + grp) * 32, sweeps);
     if (gvalid) {
 #pragma unroll
         for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < a.K) a.beta[j * a.K + c] = beta[s]; }
@@ -425,7 +450,7 @@ void launch_col_solve(const Geom& g, bool masked, const uint32_t* trC, const dou
     const int blocks = (int)((g.P + genes_per_block - 1) / genes_per_block);
     const int XLD = g.KP + 1;
     const size_t mats = masked ? (size_t)CD_WARPS * GPW : 1;
-    const size_t smem = mats * g.KP * XLD * 8 + CD_WARPS * GPW * 32;
+    const size_t smem = mats * g.KP * XLD * 8 + (size_t)CD_WARPS * GPW * 5 * g.KP * 8 + CD_WARPS * GPW * 32;
 #define LAUNCH_CS(SLv)                                                                                                 \
     if (masked) { opt_in_smem(k_col_solve<SLv, true>, smem); k_col_solve<SLv, true><<<blocks, CD_WARPS * 32, smem, st>>>(a); } \
     else { opt_in_smem(k_col_solve<SLv, false>, smem); k_col_solve<SLv, false><<<blocks, CD_WARPS * 32, smem, st>>>(a); }
@@ -442,7 +467,7 @@ void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const dou
     a.als_iter = als_iter; a.gene0 = gene0;
     const int genes_per_block = CD_WARPS * GPW;
     const int blocks = (int)((n + genes_per_block - 1) / genes_per_block);
-    const size_t smem = (size_t)CD_WARPS * GPW * a.KP * (a.KP + 1) * 8 + CD_WARPS * GPW * 32;
+    const size_t smem = (size_t)CD_WARPS * GPW * a.KP * (a.KP + 1) * 8 + (size_t)CD_WARPS * GPW * 5 * a.KP * 8 + CD_WARPS * GPW * 32;
 #define LAUNCH_CB(SLv) { opt_in_smem(k_cd_batch<SLv>, smem); k_cd_batch<SLv><<<blocks, CD_WARPS * 32, smem, st>>>(a); }
     switch (a.KP / 8) { case 1: LAUNCH_CB(1) break; case 2: LAUNCH_CB(2) break; case 3: LAUNCH_CB(3) break; default: LAUNCH_CB(4) break; }
 #undef LAUNCH_CB

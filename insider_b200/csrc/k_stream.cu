@@ -33,6 +33,7 @@ struct StreamArgs {
     int R, n_slabs, pitchS, pitchU;
     int n_stages;
     int n_splits;                // k_row_b: gene splits (grid.x); others: number of blocks
+    int scratch_sep;             // k_col_xty: 1 = dedicated cross-warp scratch (stage buffer too small to alias)
 };
 
 // balanced partition of n items over parts
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     const int stage_doubles = ysz + (RESIDENT_U ? 0 : usz);
     double* Ures = reinterpret_cast<double*>(smem_raw);                       // resident Ut (if any)
     double* stage0 = Ures + (RESIDENT_U ? usz : 0);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)S * stage_doubles);   // S stage barriers + 1 for Ut
+    double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [NWARPS][NT*2*64] when scratch_sep
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers + 1 for Ut
 
     if (tid == 0) {
         for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
         }
         if (slab == a.n_slabs - 1) {
             // cross-warp reduction in a fixed order, then store the K x 16 tile of Xty. The scratch
-            // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer.
-            double* scratch = Ys;
+            // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer when that is large enough.
+            double* scratch = a.scratch_sep ? scratch_own : Ys;
             __syncthreads();
             double* sc = scratch + warp * (NT * 2 * 64);
 #pragma unroll
@@ -481,10 +483,13 @@ void launch_col_xty(const Geom& g, bool masked, const double* Y, const uint32_t*
                     cudaStream_t st) {
     StreamArgs a = base_args(g);
     a.Y = Y; a.trC = trC; a.Ut = Ut; a.out = Xty; a.n_splits = n_blocks;
-    const size_t fixed = 8 * 8;
+    const size_t need = (size_t)NWARPS * g.NT * 2 * 64;                       // cross-warp scratch, doubles
+    const bool small = (size_t)TG * g.ldY < need;                             // resident path's stage cannot hold it
+    const size_t fixed = 8 * 8 + (small ? need * 8 : 0);
     const bool res = resident_geometry(g, a, 0, fixed);
     const size_t stage = ((size_t)TG * a.pitchS + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
-    const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + fixed;
+    a.scratch_sep = (stage / 8 < need) ? 1 : 0;
+    const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + 8 * 8 + (a.scratch_sep ? need * 8 : 0);
 #define LAUNCH_CX(NTv, M, RS) { set_smem(k_col_xty<NTv, M, RS>, smem); k_col_xty<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a); }
 #define LAUNCH_CX2(NTv)                                                       \
     if (masked) { if (res) LAUNCH_CX(NTv, true, true) else LAUNCH_CX(NTv, true, false) } \

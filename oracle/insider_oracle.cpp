@@ -23,7 +23,7 @@
 //
 // Permutation modes for the coordinate order (coordinate_descent.cpp:89):
 //   mode 0 (A) R-stream-faithful: one global R RNG consumed gene after gene (single-thread semantics).
-//   mode 1 (B) counter-based: keys (seed, als_iter, gene, draw) -> 31-bit values, sorted ascending with
+//   mode 1 (B) counter-based: keys (seed, als_iter, gene, draw) -> 26-bit values, sorted ascending with
 //              index tie-break. Identical on CPU and GPU; parity at scale is defined in this mode.
 //   mode 2     identity order (no shuffling) - for analytic tests.
 
@@ -115,7 +115,7 @@ void randperm(PermSrc& ps, int n, int* ord) {
     } else if (ps.mode == 1) {
         uint64_t key = mix64(ps.seed + 0x9E3779B97F4A7C15ull * (1ull + ps.als_iter)) ^
                        mix64(ps.gene * 0xD1B54A32D192ED03ull + (uint64_t)ps.draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
-        for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)) >> 33), i};
+        for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)) >> 38), i};
     } else {
         for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)i, i};
     }

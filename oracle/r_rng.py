@@ -182,5 +182,5 @@ def randperm_b(seed: int, als_iter: int, gene: int, draw: int, n: int) -> np.nda
 
     key = mix64(seed + 0x9E3779B97F4A7C15 * (1 + als_iter)) ^ mix64(
         gene * 0xD1B54A32D192ED03 + draw * 0x8CB92BA72F3D8DD7 + 0x2545F4914F6CDD1D)
-    vals = np.array([mix64(key + 0x9E3779B97F4A7C15 * (i + 1)) >> 33 for i in range(n)], dtype=np.int64)
+    vals = np.array([mix64(key + 0x9E3779B97F4A7C15 * (i + 1)) >> 38 for i in range(n)], dtype=np.int64)
     return np.argsort(vals, kind="stable")

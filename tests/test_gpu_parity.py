@@ -1,0 +1,306 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs and
+against the committed golden fixtures.
+
+Stated tolerances (FP64; BASELINE.json north_star asks for 1e-8 relative per iteration and an identical convergence
+iteration count):
+  * factors (every A_c, W, V): max-abs error relative to the matrix's max-abs  <= 1e-8 after every compared iteration
+  * loss, train RMSE, test RMSE at every evaluation                            <= 1e-10 relative
+  * number of ALS iterations run, number of evaluations, decay ladder values   identical
+  * coordinate-descent sweep totals                                            identical where asserted (they are, on
+    these fixtures: the GPU evaluates the same loss differences without cancellation, see csrc/k_cd.cu)
+  * train/test split mask                                                      bit-exact
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from insider_b200 import _cabi, api, synth
+from oracle import oracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import make_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FACTOR_TOL, SCALAR_TOL = 1e-8, 1e-10
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(b).max()))
+
+
+def gpu_optimize(ctx, pb, tr, te, F0, V0, K, lam, alpha, tuning, iters, seed, gtol=1e-12, stol=1e-5, perm=_cabi.PERM_COUNTER, X=None):
+    prob = _cabi.HostProblem(pb.Y, pb.confounder, X, tr, te, 1 if X is not None else 0)
+    fac = _cabi.HostFactors(F0, V0, K)
+    opt = _cabi.default_options()
+    opt.lambda1 = opt.lambda2 = lam
+    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed, opt.perm_mode = alpha, tuning, gtol, stol, iters, seed, perm
+    res = ctx.optimize(prob, fac, opt)
+    return res, fac
+
+
+def assert_parity(res, fac, ro, tuning, sweeps_equal=True):
+    assert res["iters_run"] == ro.iters_run
+    assert len(res["checks"]) == len(ro.checks)
+    assert rel(fac.V, ro.column_factor) <= FACTOR_TOL
+    for a, b in zip(fac.factors, ro.factors):
+        assert rel(a, b) <= FACTOR_TOL
+    for cg, co in zip(res["checks"], ro.checks):
+        assert cg["iter"] == co["iter"]
+        assert abs(cg["loss"] - co["loss"]) <= SCALAR_TOL * abs(co["loss"])
+        assert abs(cg["train_rmse"] - co["train_rmse"]) <= SCALAR_TOL * co["train_rmse"]
+        assert cg["decay"] == co["decay"]
+        if tuning == 1:
+            assert abs(cg["test_rmse"] - co["test_rmse"]) <= SCALAR_TOL * co["test_rmse"]
+        else:
+            assert np.isnan(cg["test_rmse"])
+    if sweeps_equal:
+        assert res["cd_sweeps"] == ro.cd_sweeps
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_gpu_matches_golden_and_oracle(ctx, name):
+    N, P, K, tuning, alpha, lam, Q, iters = make_golden.CASES[name]
+    pb, tr, te, F0, V0 = make_golden.make_inputs(name)
+    res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, lam, alpha, tuning, iters, 77, X=pb.X if Q else None)
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    assert res["iters_run"] == int(g["iters_run"])
+    assert res["cd_sweeps"] == int(g["cd_sweeps"])
+    assert rel(fac.V, g["V"]) <= FACTOR_TOL
+    for i, f in enumerate(fac.factors):
+        assert rel(f, g[f"F{i}"]) <= FACTOR_TOL
+    np.testing.assert_allclose([c["loss"] for c in res["checks"]], g["check_loss"], rtol=SCALAR_TOL)
+    ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, pb.X, tr, te, 1 if Q else 0, K, lam, lam, alpha, tuning, 1e-12, 1e-5, iters, perm_mode=1, seed=77)
+    assert_parity(res, fac, ro, tuning)
+
+
+@pytest.mark.parametrize("tuning", [0, 1])
+@pytest.mark.parametrize("K", [1, 8, 9, 16, 23, 24, 30, 32])
+def test_every_latent_dim_tile_count(ctx, K, tuning):
+    """K spans all four DMMA tile counts (KP = 8, 16, 24, 32) including exact multiples and the maximum."""
+    N, P = 57, 83                                         # ragged: neither a multiple of 8/32 rows nor of 16 genes
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=9, seed=K)
+    tr, te = synth.random_masks(N, P, 0.15, K + 1)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=K + 2)
+    ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 2.5, 2.5, 0.35, tuning, 1e-12, 1e-5, 6, perm_mode=1, seed=5)
+    res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 2.5, 0.35, tuning, 6, 5)
+    assert_parity(res, fac, ro, tuning)
+
+
+@pytest.mark.parametrize("tuning", [0, 1])
+def test_per_iteration_parity_through_stepping_interface(ctx, tuning):
+    """Factors after EVERY iteration (north_star: 1e-8 per iteration) via insider_b200_als_step/_read."""
+    N, P, K = 377, 320, 23
+    pb = synth.ageing_like(N=N, P=P, K=K, seed=3)
+    tr, te = synth.random_masks(N, P, 0.1, 4)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=5)
+    prob = _cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0)
+    res = ctx.upload(prob)
+    opt = _cabi.default_options()
+    opt.lambda1 = opt.lambda2 = 10.0
+    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = 0.4, tuning, 1e-12, 1e-5, 100, 21
+    fac = _cabi.HostFactors(F0, V0, K)
+    s = res.begin(fac, opt)
+    for it in range(1, 8):
+        s.step(1)
+        Fg, Vg = s.read()
+        ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 10.0, 10.0, 0.4, tuning, 1e-12, 1e-5, it - 1, perm_mode=1, seed=21)
+        assert rel(Vg, ro.column_factor) <= FACTOR_TOL, it
+        for a, b in zip(Fg, ro.factors):
+            assert rel(a, b) <= FACTOR_TOL, it
+    out = s.end()
+    assert out["iters_run"] == 7
+    res.release()
+
+
+def test_multi_slab_rows(ctx):
+    """N > 384 exercises the row-slab geometry of the streaming kernels (k_row_b 384-row slabs, k_col_xty/k_sse 128-row)."""
+    for N, P, K in [(385, 40, 6), (900, 70, 12), (1100, 50, 20)]:
+        pb = synth.ageing_like(N=N, P=P, K=K, n_donors=31, seed=N)
+        tr, te = synth.random_masks(N, P, 0.1, 1)
+        F0, V0 = synth.init_factors(pb.levels, K, P, seed=2)
+        for tuning in (0, 1):
+            ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 4.0, 4.0, 0.4, tuning, 1e-12, 1e-5, 3, perm_mode=1, seed=8)
+            res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 4.0, 0.4, tuning, 3, 8)
+            assert_parity(res, fac, ro, tuning)
+
+
+def test_mask_dtypes_and_heavy_masking(ctx):
+    """int32 (R integer), uint8 and double masks give identical results; rows/genes that are almost fully masked."""
+    N, P, K = 64, 96, 7
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=9, seed=9)
+    rng = np.random.default_rng(4)
+    test = rng.random((N, P)) < 0.1
+    train = ~test
+    train[5, :] = False; train[5, :3] = True             # a row with 3 observed entries
+    train[:, 11] = False; train[:4, 11] = True           # a gene with 4 observed entries
+    train[:, 12] = False                                 # a gene with no training entry at all
+    test[:, 12] = False
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=3)
+    ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, train.astype(np.int32), test.astype(np.int32), 0, K, 2.0, 2.0, 0.4, 1, 1e-12, 1e-5, 5,
+                         perm_mode=1, seed=1)
+    outs = []
+    for dt in (np.int32, np.uint8, np.float64):
+        res, fac = gpu_optimize(ctx, pb, np.asfortranarray(train.astype(dt)), np.asfortranarray(test.astype(dt)), F0, V0, K, 2.0, 0.4, 1, 5, 1)
+        assert_parity(res, fac, ro, 1)
+        outs.append(fac.V.copy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.all(outs[0][:, 12] == 0.0)                 # gene without data: Xty = 0 -> screened to exactly zero
+
+
+def test_identity_permutation_mode_and_run_to_run_determinism(ctx):
+    N, P, K = 50, 60, 6
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=9, seed=2)
+    tr, te = synth.random_masks(N, P, 0.1, 3)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=4)
+    ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 2.0, 2.0, 0.5, 1, 1e-12, 1e-5, 8, perm_mode=2, seed=0)
+    res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 2.0, 0.5, 1, 8, 0, perm=_cabi.PERM_IDENTITY)
+    assert_parity(res, fac, ro, 1)
+    res2, fac2 = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 2.0, 0.5, 1, 8, 0, perm=_cabi.PERM_IDENTITY)
+    assert np.array_equal(fac.V, fac2.V) and all(np.array_equal(a, b) for a, b in zip(fac.factors, fac2.factors))   # fixed-order reductions
+    assert res["loss"] == res2["loss"]
+
+
+def test_convergence_iteration_count_matches(ctx):
+    """Run to global_tol: same break iteration, same decay ladder, loss/RMSE within tolerance (north_star)."""
+    N, P, K = 120, 300, 8
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=21, seed=12)
+    tr, te = synth.random_masks(N, P, 0.1, 13)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=14)
+    for tuning in (0, 1):
+        ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 5.0, 5.0, 0.4, tuning, 1e-6, 1e-5, 2000, perm_mode=1, seed=3)
+        res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 5.0, 0.4, tuning, 2000, 3, gtol=1e-6)
+        assert ro.iters_run < 2000
+        assert res["iters_run"] == ro.iters_run
+        assert [c["decay"] for c in res["checks"]] == [c["decay"] for c in ro.checks]
+        assert abs(res["loss"] - ro.loss) <= 1e-8 * ro.loss
+        assert rel(fac.V, ro.column_factor) <= 1e-6       # late sweeps run at tol*decay near FP noise: see DESIGN.md "stopping rule"
+        if tuning == 1:
+            assert abs(res["test_rmse"] - ro.test_rmse) <= 1e-8 * ro.test_rmse
+
+
+def test_batched_strong_cd_entry(ctx):
+    """insider_b200_strong_cd against the oracle's strong_coordinate_descent on the same (XtX, Xty, wstart, order)."""
+    rng = np.random.default_rng(6)
+    K, n_cols, n = 23, 257, 90
+    X = rng.normal(size=(n, K)); G = X.T @ X
+    Y = X @ (rng.normal(size=(K, n_cols)) * (rng.random((K, n_cols)) < 0.5)) + 0.2 * rng.normal(size=(n, n_cols))
+    Xty = X.T @ Y
+    w0 = 0.01 * rng.normal(size=(K, n_cols))
+    for alpha, lam in [(0.4, 10.0), (1.0, 4.0), (0.05, 30.0)]:
+        beta, sweeps = ctx.strong_cd(G, Xty, w0, lam, alpha, tol=1e-7, seed=5, als_iter=2, gene0=100)
+        for j in range(0, n_cols, 7):
+            bo, sw, _ = oracle.strong_cd(X, Y[:, j], w0[:, j], lam, alpha, G, Xty[:, j], tol=1e-7, perm_mode=1, seed=5, als_iter=2, gene=100 + j)
+            assert rel(beta[:, j], bo) <= 1e-9 or np.abs(beta[:, j] - bo).max() < 1e-12
+            assert sweeps[j] == sw
+    # per-column Gram matrices (the masked path's shape)
+    Gs = np.stack([G + np.diag(rng.random(K)) for _ in range(n_cols)])
+    beta, sweeps = ctx.strong_cd(Gs, Xty, w0, 5.0, 0.3, tol=1e-6, perm_mode=_cabi.PERM_IDENTITY)
+    la, l2 = 5.0 * 0.3, 5.0 * 0.7
+    for j in range(0, n_cols, 31):                       # KKT of the covariance-form problem
+        grad = Xty[:, j] - Gs[j] @ beta[:, j] - l2 * beta[:, j]
+        on = beta[:, j] != 0
+        assert np.all(np.abs(grad[on] - la * np.sign(beta[on, j])) < 2e-2)
+        assert np.all(np.abs(grad[~on]) <= la + 2e-2)
+
+
+def test_fit_interaction_entry(ctx):
+    rng = np.random.default_rng(8)
+    N, P, K, L = 60, 130, 5, 7
+    V = rng.normal(size=(K, P)); R = rng.normal(size=(N, P))
+    z = np.concatenate([np.arange(1, L + 1), rng.integers(1, L + 1, N - L)]).astype(np.int32)
+    tr = np.asfortranarray((rng.random((N, P)) < 0.9).astype(np.int32))
+    for tuning in (0, 1):
+        got = ctx.fit_interaction(R, tr, L, z, V, tuning)
+        want = oracle.fit_interaction(R, tr, L, z, V, tuning)
+        assert rel(got, want) <= 1e-10
+
+
+def test_error_codes(ctx):
+    N, P, K = 20, 16, 3
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=5, seed=1)
+    tr, te = synth.random_masks(N, P, 0.2, 1)
+    F0, V0 = synth.init_factors(pb.levels, K, P)
+    with pytest.raises(_cabi.InsiderError) as e:         # tuning must be 0/1 (reference: exit(1), src/optimize.cpp:193-195)
+        gpu_optimize(ctx, pb, tr, te, F0, V0, K, 1.0, 0.1, 2, 3, 0)
+    assert e.value.code == _cabi.ERR_INVALID_ARG
+    with pytest.raises(_cabi.InsiderError) as e:         # empty test set with tuning=1 (reference: arma::mean throws)
+        gpu_optimize(ctx, pb, tr, np.zeros_like(te), F0, V0, K, 1.0, 0.1, 1, 3, 0)
+    assert e.value.code == _cabi.ERR_EMPTY_TEST_SET
+    bad = synth.SynthProblem(pb.Y, pb.confounder + 1, None, pb.levels)
+    with pytest.raises(_cabi.InsiderError) as e:         # levels must be exactly 1..L_c
+        gpu_optimize(ctx, bad, tr, te, F0, V0, K, 1.0, 0.1, 1, 3, 0)
+    assert e.value.code == _cabi.ERR_INVALID_ARG
+    F33, V33 = synth.init_factors(pb.levels, 33, P)
+    with pytest.raises(_cabi.InsiderError) as e:
+        gpu_optimize(ctx, pb, tr, te, F33, V33, 33, 1.0, 0.1, 1, 3, 0)
+    assert e.value.code == _cabi.ERR_UNSUPPORTED
+    with pytest.raises(_cabi.InsiderError) as e:         # a non-SPD system (lambda = 0, rank-deficient) is reported, not silently "solved"
+        gpu_optimize(ctx, pb, None, None, [np.zeros_like(f) for f in F0], np.zeros_like(V0), K, 0.0, 0.0, 0, 1, 0)
+    assert e.value.code in (_cabi.ERR_NOT_SPD, _cabi.ERR_DIVERGED)
+
+
+def test_api_mirror_insider_tune_fit(ctx, tmp_path, monkeypatch):
+    """insider() / tune() / fit() with the reference's object layout; masks bit-exact with R's sample()."""
+    from oracle.r_rng import ratio_splitter
+    monkeypatch.chdir(tmp_path)
+    api.set_default_context(ctx)
+    pb = synth.ageing_like(N=90, P=150, K=4, n_donors=12, interaction=False, seed=3)
+    obj = api.insider(pb.Y, pb.confounder, None, np.array([1, 2]), split_ratio=0.1, tuning_iter=10, max_iter=40, global_tol=1e-7)
+    s = ratio_splitter(pb.Y, 0.1, rm_na_col=False, seed=123)
+    assert np.array_equal(obj["train_indicator"] != 0, s["train_indicator"]) and np.array_equal(obj["test_indicator"] != 0, s["test_indicator"])
+    assert obj["confounder"].shape[1] == pb.confounder.shape[1] + 1 and obj["inc_continuous"] == 0
+    assert set(obj["params"]) == {"global_tol", "sub_tol", "tuning_iter", "max_iter"}
+    t = api.tune(obj, np.array([2, 4], dtype=np.int64), np.array([1.0, 3.0]), np.array([0.2, 0.4]), seed=1)
+    assert t["rank_tuning"].shape == (2, 3) and t["reg_tuning"].shape == (4, 4) and t["latent_rank"] in (2, 4)
+    assert t["reg_tuning"][:, 0].tolist() == [1.0, 3.0, 1.0, 3.0]                    # expand.grid: lambda fastest
+    assert os.path.exists("insider_rank_tuning_result.csv") and os.path.exists(f"insider_R{t['latent_rank']}_reg_tuning_result.csv")
+    obj = api.fit(obj, 4, 3.0, 0.4, partition=0, seed=2)
+    assert sorted(obj["cfd_matrices"]) == [f"factor{i}" for i in range(obj["confounder"].shape[1])]
+    assert obj["column_factor"].shape == (4, 150) and np.isnan(obj["test_rmse"])
+    info = obj["fit_info"]
+    ro = oracle.optimize(obj["data"], *synth_init_like(obj, 4, 2), obj["confounder"], None, None, None, 0, 4, 3.0, 3.0, 0.4, 0, 1e-7, 1e-5, 40, perm_mode=1, seed=2)
+    assert info["iters_run"] == ro.iters_run and abs(info["loss"] - ro.loss) <= 1e-9 * ro.loss
+
+
+def synth_init_like(obj, K, seed):
+    rng = np.random.default_rng(seed)
+    return api._init_factors(obj, K, rng)
+
+
+@pytest.mark.parametrize("tuning", [0, 1])
+def test_full_size_properties(ctx, tuning):
+    """377 x 44477, K = 23 (BASELINE config 2/3 shape): size-independent properties instead of an oracle run.
+    (1) loss non-increasing over checks, (2) a second run is bitwise identical, (3) every gene satisfies the elastic-net
+    KKT conditions of its own sub-problem, checked on a sample of genes with NumPy, (4) factors rebuilt by the row
+    update satisfy the per-level normal equations."""
+    N, P, K, lam, alpha = 377, 44477, 23, 10.0, 0.4
+    pb = synth.ageing_like(N=N, P=P, K=K)
+    tr, te = synth.random_masks(N, P, 0.1, 1)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=2)
+    prob = _cabi.HostProblem(pb.Y, pb.confounder, None, tr if tuning else None, te if tuning else None, 0)
+    res = ctx.upload(prob)
+    opt = _cabi.default_options()
+    opt.lambda1 = opt.lambda2 = lam
+    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = alpha, tuning, 1e-12, 1e-5, 20, 4
+    fac = _cabi.HostFactors(F0, V0, K)
+    out = res.optimize(fac, opt)
+    losses = [c["loss"] for c in out["checks"]]
+    assert out["iters_run"] == 21 and all(b <= a for a, b in zip(losses, losses[1:]))
+    fac2 = _cabi.HostFactors(F0, V0, K)
+    out2 = res.optimize(fac2, opt)
+    assert np.array_equal(fac.V, fac2.V) and out2["loss"] == out["loss"]
+    res.release()
+    U = sum(fac.factors[c][pb.confounder[:, c] - 1] for c in range(len(pb.levels)))
+    la, l2 = lam * alpha, lam * (1 - alpha)
+    rng = np.random.default_rng(0)
+    for j in rng.choice(P, 200, replace=False):
+        m = tr[:, j] != 0 if tuning else np.ones(N, bool)
+        grad = U[m].T @ (pb.Y[m, j] - U[m] @ fac.V[:, j]) - l2 * fac.V[:, j]
+        on = fac.V[:, j] != 0
+        # the last inner sweep stopped at |delta loss| <= 1e-5: gradients are within sqrt(2 tol XtX_kk) of optimal
+        slack = np.sqrt(2e-5 * (U[m] ** 2).sum(axis=0)) + 1e-9
+        assert np.all(np.abs(grad[on] - la * np.sign(fac.V[on, j])) <= 40 * slack[on])
+        assert np.all(np.abs(grad[~on]) <= la + 40 * slack[~on])

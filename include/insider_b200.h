@@ -102,7 +102,7 @@ typedef struct {
     uint32_t check_every;            /* 0 -> 10 (src/optimize.cpp:381) */
     uint64_t seed;                   /* permutation seed (the Rcpp shim draws it from R's RNG inside RNGScope) */
     int32_t verbose;                 /* 1: print the reference's per-check lines to stdout */
-    int32_t use_graph;               /* 1: replay the iteration as a CUDA graph (default 1 when 0 is passed? no: -1 = auto) */
+    int32_t use_graph;               /* >= 0 (default): replay each ALS iteration as a CUDA graph; -1: plain kernel launches */
 } insider_options;
 
 /* one record per evaluation: the initial one (iter = -1, src/optimize.cpp:320-323) and every check_every-th iteration */

@@ -2,7 +2,6 @@
 //
 //   k_gram_v         gram = V V^T                                   src/optimize.cpp:332
 //   k_row_comp_gram  per-row complement  sum_{j: m_ij=0} v_j v_j^T  src/optimize.cpp:163,170 (c_factor.cols(zero_idx) * trans(..))
-//   k_gram_u         U^T U                                          src/optimize.cpp:205 / :234
 //   k_reduce         deterministic sum of per-block partial buffers
 #include "common.cuh"
 #include "kernels.cuh"
@@ -111,24 +110,6 @@ __global__ void __launch_bounds__(256) k_reduce(double* __restrict__ out, const 
     out[i] = s;
 }
 
-// partial U^T U over a chunk of 256 rows
-__global__ void __launch_bounds__(256) k_gram_u(const double* __restrict__ U, double* __restrict__ parts, int N, int KP) {
-    const int r0 = blockIdx.x * 256, r1 = min(N, r0 + 256);
-    for (int e = threadIdx.x; e < KP * KP; e += 256) {
-        const int a = e / KP, b = e % KP;
-        double s = 0.0;
-        for (int i = r0; i < r1; ++i) s = fma(U[(size_t)i * KP + a], U[(size_t)i * KP + b], s);
-        parts[(size_t)blockIdx.x * KP * KP + e] = s;
-    }
-}
-__global__ void __launch_bounds__(256) k_gram_u_final(const double* __restrict__ parts, double* __restrict__ UtU, int n_parts, int KP) {
-    for (int e = threadIdx.x; e < KP * KP; e += 256) {
-        double s = 0.0;
-        for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * KP * KP + e];
-        UtU[e] = s;
-    }
-}
-
 }  // namespace
 
 void launch_gram_v(const Geom& g, const double* V, double* Gp, int n_blocks, cudaStream_t st) {
@@ -150,14 +131,6 @@ void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, d
 void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st) {
     const int blocks = (int)((n_elems + 255) / 256);
     k_reduce<<<blocks, 256, 0, st>>>(out, partials, n_elems, n_parts);
-}
-
-void launch_gram_u(const Geom& g, const double* U, double* UtU, cudaStream_t st) {
-    // partial buffer lives right after UtU (caller allocates (1 + ceil(N/256)) * KP*KP doubles)
-    const int n_parts = (g.N + 255) / 256;
-    double* parts = UtU + (size_t)g.KP * g.KP;
-    k_gram_u<<<n_parts, 256, 0, st>>>(U, parts, g.N, g.KP);
-    k_gram_u_final<<<1, 256, 0, st>>>(parts, UtU, n_parts, g.KP);
 }
 
 }  // namespace ib

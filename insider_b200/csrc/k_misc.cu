@@ -52,7 +52,7 @@ __global__ void k_sse_reduce(const double* __restrict__ partial, int n_blocks, C
 }
 
 // src/utils.cpp:56-102 (rmse, loss terms) and src/optimize.cpp:381-408 (delta, decay ladder, convergence)
-__global__ void __launch_bounds__(256) k_check(CheckState* st, const double* __restrict__ A_all, int64_t n_A, int initial, insider_check* rec) {
+__global__ void __launch_bounds__(256) k_check(CheckState* st, const double* __restrict__ A_all, int64_t n_A, int initial, int iter, insider_check* rec) {
     __shared__ double red[256];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n_A; i += 256) s = fma(A_all[i], A_all[i], s);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_check(CheckState* st, const double* __r
     st->diverged = isfinite(loss) ? 0 : 1;
     st->row_reg = row_reg; st->train_rmse = train_rmse; st->test_rmse = test_rmse; st->delta_loss = delta;
     if (rec) {
-        rec->iter = initial ? -1 : (int32_t)st->als_iter; rec->pad = 0;
+        rec->iter = initial ? -1 : iter; rec->pad = 0;
         rec->sum_residual = sse; rec->train_rmse = train_rmse; rec->test_rmse = test_rmse;
         rec->row_reg = row_reg / 2; rec->col_reg = col_reg / 2; rec->l1_reg = l1_reg; rec->loss = loss; rec->delta_loss = delta; rec->decay = decay;
     }
@@ -120,8 +120,8 @@ void launch_count_bits(const uint32_t* m, int64_t n_words, unsigned long long* o
 
 void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, cudaStream_t st) { k_sse_reduce<<<1, 32, 0, st>>>(partial, n_blocks, state); }
 
-void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, void* record_out, cudaStream_t st) {
-    k_check<<<1, 256, 0, st>>>(state, A_all, n_A, initial, (insider_check*)record_out);
+void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, int iter, void* record_out, cudaStream_t st) {
+    k_check<<<1, 256, 0, st>>>(state, A_all, n_A, initial, iter, (insider_check*)record_out);
 }
 
 void launch_bump_iter(CheckState* state, cudaStream_t st) { k_bump_iter<<<1, 1, 0, st>>>(state); }

@@ -7,7 +7,11 @@
 // the normal equations of level s of confounder c (src/optimize.cpp:150-176 / :178-191) are
 //     XtX_s = sum_{k in s} Gk_k + lambda I ,   Xty_s = sum_{k in s} [ B_k - Gk_k (u_k - a_{c,s}) ]
 // where u_k is the current row factor (Gauss-Seidel: blocks updated earlier in the same iteration are already in u_k).
-// In the dense path (tuning = 0) Gk_k = G for every row.
+// In the dense path (tuning = 0) Gk_k = G for every row, so Xty_s = sum B_k - G (sum u_k - n_s a_s).
+//
+// XtX_s does not depend on the factors, so all levels of all confounders are assembled and Cholesky-factorised up front
+// by one launch (k_level_factor: one warp per level, batched K x K factorisations in shared memory); the per-confounder
+// launches then only form right-hand sides, substitute, and shift the rows of U.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -15,7 +19,9 @@ namespace ib {
 
 namespace {
 
-// shared with k_cd.cu in spirit: warp Cholesky on an odd-pitch shared matrix
+constexpr int LG_ROWS = 32;      // rows per k_level_gram chunk
+
+// warp Cholesky on an odd-pitch shared matrix (lane = row)
 __device__ bool chol_factor(double* S, int ld, int K, int lane) {
     bool ok = true;
     for (int j = 0; j < K; ++j) {
@@ -48,21 +54,74 @@ __device__ double chol_subst(const double* S, int ld, int K, int lane, double b)
     }
     return b;
 }
+// substitution with a stored factor: Lf[KP*KP] row-major lower triangle, Lf[KP*KP + i] = 1 / L_ii
+__device__ double chol_subst_stored(const double* __restrict__ Lf, int KP, int K, int lane, double b) {
+    const double* inv = Lf + KP * KP;
+    for (int i = 0; i < K; ++i) {
+        double xi = b * inv[i];
+        xi = __shfl_sync(FULL, xi, i);
+        if (lane == i) b = xi;
+        else if (lane > i && lane < K) b = fma(-Lf[lane * KP + i], xi, b);
+    }
+    for (int i = K - 1; i >= 0; --i) {
+        double xi = b * inv[i];
+        xi = __shfl_sync(FULL, xi, i);
+        if (lane == i) b = xi;
+        else if (lane < i) b = fma(-Lf[i * KP + lane], xi, b);
+    }
+    return b;
+}
 
-// GL[s][e] = sum_{k in s} (G[e] - D[k][e])
-__global__ void __launch_bounds__(256) k_level_gram(const int* __restrict__ rows_sorted, const int* __restrict__ level_start,
-                                                    const double* __restrict__ G, const double* __restrict__ D, double* __restrict__ GL, int KK) {
-    const int s = blockIdx.x;
-    const int b = level_start[s], e = level_start[s + 1];
+// masked path: GLp[level][chunk][e] = sum over the chunk's rows of (G[e] - D[row][e]); grid (total levels, max chunks)
+__global__ void __launch_bounds__(256) k_level_gram(const LevelTable* __restrict__ tab, const double* __restrict__ G, const double* __restrict__ D,
+                                                    double* __restrict__ GLp, int KK, int max_chunks) {
+    __shared__ int rows[LG_ROWS];
+    const LevelTable t = tab[blockIdx.x];
+    const int b = t.row_begin + blockIdx.y * LG_ROWS, e = min(t.row_end, b + LG_ROWS);
+    if (b >= e) return;
+    if (threadIdx.x < e - b) rows[threadIdx.x] = t.rows_sorted[b + threadIdx.x];
+    __syncthreads();
+    const int n = e - b;
+    double* out = GLp + ((size_t)blockIdx.x * max_chunks + blockIdx.y) * KK;
     for (int x = threadIdx.x; x < KK; x += 256) {
         const double gx = G[x];
         double acc = 0.0;
-        for (int r = b; r < e; ++r) acc += gx - D[(size_t)rows_sorted[r] * KK + x];
-        GL[(size_t)s * KK + x] = acc;
+#pragma unroll 4
+        for (int r = 0; r < n; ++r) acc += gx - D[(size_t)rows[r] * KK + x];
+        out[x] = acc;
     }
 }
 
-// warp per row: T_k = B_k - M_k (u_k - a), M_k = G - D_k (masked) or G. `sub_own` = 0 drops the "- a" term (continuous block).
+// one warp per level (all confounders): assemble XtX_s + lambda I, factorise, store L and 1/diag
+__global__ void __launch_bounds__(32) k_level_factor(const LevelTable* __restrict__ tab, int K, int KP, int masked, const double* __restrict__ G,
+                                                     const double* __restrict__ GLp, int max_chunks, double lambda, double* __restrict__ Lfac,
+                                                     int* err_flag) {
+    extern __shared__ double S[];                      // [KP][KP+1]
+    const int ld = KP + 1, KK = KP * KP, lane = threadIdx.x;
+    const LevelTable t = tab[blockIdx.x];
+    const int n_rows = t.row_end - t.row_begin;
+    const int n_chunks = (n_rows + LG_ROWS - 1) / LG_ROWS;
+    for (int x = lane; x < KK; x += 32) {
+        const int r = x / KP, c = x % KP;
+        double v;
+        if (masked) {                                                          // optimize.cpp:170
+            v = 0.0;
+            for (int y = 0; y < n_chunks; ++y) v += GLp[((size_t)blockIdx.x * max_chunks + y) * KK + x];
+        } else {
+            v = (double)n_rows * G[x];                                         // :186
+        }
+        if (r == c) v += lambda;                                               // :174 / :187
+        S[r * ld + c] = v;
+    }
+    __syncwarp();
+    const bool ok = chol_factor(S, ld, K, lane);
+    if (!ok && lane == 0) atomicExch(err_flag, 1);
+    double* out = Lfac + (size_t)blockIdx.x * (KK + KP);
+    for (int x = lane; x < KK; x += 32) out[x] = S[(x / KP) * ld + (x % KP)];
+    if (lane < KP) out[KK + lane] = (lane < K) ? 1.0 / S[lane * ld + lane] : 0.0;
+}
+
+// masked path: warp per row, T_k = B_k - (G - D_k)(u_k - a_{c,z(k)})
 __global__ void __launch_bounds__(256) k_row_rhs(int N, int KP, const int* __restrict__ level_of_row, const double* __restrict__ A,
                                                  const double* __restrict__ B, const double* __restrict__ G, const double* __restrict__ D,
                                                  const double* __restrict__ U, double* __restrict__ T) {
@@ -70,52 +129,62 @@ __global__ void __launch_bounds__(256) k_row_rhs(int N, int KP, const int* __res
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= N) return;
     double w = 0.0;
-    if (lane < KP) {
-        w = U[(size_t)k * KP + lane];
-        if (A) w -= A[(size_t)level_of_row[k] * KP + lane];
-    }
+    if (lane < KP) w = U[(size_t)k * KP + lane] - A[(size_t)level_of_row[k] * KP + lane];
     double acc = 0.0;
-    const double* Dk = D ? D + (size_t)k * KP * KP : nullptr;
+    const double* Dk = D + (size_t)k * KP * KP;
     for (int m = 0; m < KP; ++m) {
         const double wm = __shfl_sync(FULL, w, m);
-        if (lane < KP) {
-            double mv = G[m * KP + lane];                 // symmetric: column m read as row m (coalesced)
-            if (Dk) mv -= Dk[m * KP + lane];
-            acc = fma(mv, wm, acc);
-        }
+        if (lane < KP) acc = fma(G[m * KP + lane] - Dk[m * KP + lane], wm, acc);   // symmetric: column m read as row m (coalesced)
     }
     if (lane < KP) T[(size_t)k * KP + lane] = B[(size_t)k * KP + lane] - acc;
 }
 
-// one warp per level: assemble, solve, write A, shift the rows of U
-__global__ void __launch_bounds__(32) k_level_solve(int K, int KP, int masked, const int* __restrict__ rows_sorted,
-                                                    const int* __restrict__ level_start, double* __restrict__ A, const double* __restrict__ G,
-                                                    const double* __restrict__ GL, const double* __restrict__ T, double lambda,
-                                                    double* __restrict__ U, int* err_flag) {
-    extern __shared__ double S[];                      // [KP][KP+1]
-    const int ld = KP + 1;
-    const int s = blockIdx.x, lane = threadIdx.x;
+// per level of one confounder (block of 4 warps): right-hand side, substitution with the stored factor, A and U update
+//   masked: rhs = sum_{k in s} T_k                         (T from k_row_rhs)
+//   dense : rhs = sum_{k in s} B_k - G (sum_{k in s} u_k - n_s a_s)
+__global__ void __launch_bounds__(128) k_level_update(int K, int KP, int masked, const int* __restrict__ rows_sorted,
+                                                      const int* __restrict__ level_start, double* __restrict__ A, const double* __restrict__ G,
+                                                      const double* __restrict__ B, const double* __restrict__ T, const double* __restrict__ Lfac,
+                                                      int lfac_base, double* __restrict__ U) {
+    __shared__ double part[4][2][32];
+    __shared__ double delta_s[32];
+    const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = level_start[s], e = level_start[s + 1];
     if (e == b) return;
-    const double ns = (double)(e - b);
-    for (int x = lane; x < KP * KP; x += 32) {
-        const int r = x / KP, c = x % KP;
-        double v = masked ? GL[(size_t)s * KP * KP + x] : ns * G[x];   // optimize.cpp:170 / :186
-        if (r == c) v += lambda;                                       // :174 / :187
-        S[r * ld + c] = v;
+    double p0 = 0.0, p1 = 0.0;     // masked: p0 = sum T ; dense: p0 = sum B, p1 = sum u
+    if (lane < KP) {
+        const double* src0 = masked ? T : B;
+#pragma unroll 4
+        for (int r = b + warp; r < e; r += 4) {
+            const int k = rows_sorted[r];
+            p0 += src0[(size_t)k * KP + lane];
+            if (!masked) p1 += U[(size_t)k * KP + lane];
+        }
     }
-    double rhs = 0.0;
-    if (lane < KP)
-        for (int r = b; r < e; ++r) rhs += T[(size_t)rows_sorted[r] * KP + lane];
-    __syncwarp();
-    const bool ok = chol_factor(S, ld, K, lane);
-    const double x = chol_subst(S, ld, K, lane, rhs);                  // :175 / :190
-    if (!ok && lane == 0) atomicExch(err_flag, 1);
-    if (lane < K) {
-        const double old = A[(size_t)s * KP + lane];
-        const double dlt = x - old;
-        A[(size_t)s * KP + lane] = x;
-        for (int r = b; r < e; ++r) U[(size_t)rows_sorted[r] * KP + lane] += dlt;
+    part[warp][0][lane] = p0; part[warp][1][lane] = p1;
+    __syncthreads();
+    if (warp == 0) {
+        double rhs = (part[0][0][lane] + part[1][0][lane]) + (part[2][0][lane] + part[3][0][lane]);
+        const double a_old = (lane < KP) ? A[(size_t)s * KP + lane] : 0.0;
+        if (!masked) {
+            const double su = (part[0][1][lane] + part[1][1][lane]) + (part[2][1][lane] + part[3][1][lane]);
+            const double w = su - (double)(e - b) * a_old;
+            double acc = 0.0;
+            for (int m = 0; m < KP; ++m) {
+                const double wm = __shfl_sync(FULL, w, m);
+                if (lane < KP) acc = fma(G[m * KP + lane], wm, acc);
+            }
+            rhs -= acc;
+        }
+        const double x = chol_subst_stored(Lfac + (size_t)(lfac_base + s) * (KP * KP + KP), KP, K, lane, rhs);   // :175 / :190
+        double dlt = 0.0;
+        if (lane < K) { dlt = x - a_old; A[(size_t)s * KP + lane] = x; }
+        delta_s[lane] = dlt;
+    }
+    __syncthreads();
+    if (lane < KP) {
+        const double dlt = delta_s[lane];
+        for (int r = b + warp; r < e; r += 4) U[(size_t)rows_sorted[r] * KP + lane] += dlt;
     }
 }
 
@@ -128,14 +197,12 @@ __global__ void __launch_bounds__(256) k_cont_partial(int N, int KP, const doubl
     const int r0 = blockIdx.x * 64, r1 = min(N, r0 + 64);
     const int KK = KP * KP;
     double* out = scratch + (size_t)blockIdx.x * (KK + KP);
-    // H: element-parallel, rows in order
     for (int e = tid; e < KK; e += 256) {
         const double gx = G[e];
         double acc = 0.0;
         for (int k = r0; k < r1; ++k) { const double xk = x[k]; acc = fma(xk * xk, D ? gx - D[(size_t)k * KK + e] : gx, acc); }
         out[e] = acc;
     }
-    // T: warp w takes rows r0+w, r0+w+8, ... ; then the 8 warps are combined in order
     double tacc = 0.0;
     for (int k = r0 + warp; k < r1; k += 8) {
         const double w = (lane < KP) ? U[(size_t)k * KP + lane] : 0.0;
@@ -208,34 +275,62 @@ __global__ void __launch_bounds__(256) k_cont_final(int N, int K, int KP, int ma
     }
 }
 
+// U = sum_c A_c[z_c] + X W for a chunk of 32 rows; also Ut and the chunk's partial U^T U (fixed-order reduce follows)
 __global__ void __launch_bounds__(256) k_build_u(int N, int KP, int ldT, int C, const RowDesign* __restrict__ designs, int Q,
                                                  const double* __restrict__ X, const double* __restrict__ W, double* __restrict__ U,
-                                                 double* __restrict__ Ut) {
-    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (e >= (int64_t)N * KP) return;
-    const int k = (int)(e / KP), l = (int)(e % KP);
-    double s = 0.0;
-    for (int c = 0; c < C; ++c) s += designs[c].A[(size_t)designs[c].level_of_row[k] * KP + l];      // optimize.cpp:366-369
-    for (int q = 0; q < Q; ++q) s = fma(X[(size_t)q * N + k], W[(size_t)q * KP + l], s);             // :371-373
-    U[e] = s;
-    Ut[(size_t)l * ldT + k] = s;
+                                                 double* __restrict__ Ut, double* __restrict__ UtU_parts) {
+    __shared__ double us[32][33];
+    const int r0 = blockIdx.x * 32;
+    for (int x = threadIdx.x; x < 32 * KP; x += 256) {
+        const int kr = x / KP, l = x % KP, k = r0 + kr;
+        double s = 0.0;
+        if (k < N) {
+            for (int c = 0; c < C; ++c) s += designs[c].A[(size_t)designs[c].level_of_row[k] * KP + l];   // optimize.cpp:366-369
+            for (int q = 0; q < Q; ++q) s = fma(X[(size_t)q * N + k], W[(size_t)q * KP + l], s);          // :371-373
+            U[(size_t)k * KP + l] = s;
+            Ut[(size_t)l * ldT + k] = s;
+        }
+        us[kr][l] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KP * KP; e += 256) {
+        const int a = e / KP, b = e % KP;
+        double s = 0.0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) s = fma(us[i][a], us[i][b], s);
+        UtU_parts[(size_t)blockIdx.x * KP * KP + e] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_gram_u_final(const double* __restrict__ parts, double* __restrict__ UtU, int n_parts, int KK) {
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < KK; e += gridDim.x * 256) {
+        double s = 0.0;
+        for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * KK + e];
+        UtU[e] = s;
+    }
 }
 
 }  // namespace
 
-void launch_level_gram(const Geom& g, const RowDesign& d, const double* G, const double* D, double* GL, cudaStream_t st) {
-    k_level_gram<<<d.L, 256, 0, st>>>(d.rows_sorted, d.level_start, G, D, GL, g.KP * g.KP);
+void launch_level_gram(const Geom& g, const LevelTable* tab_dev, int total_levels, int max_chunks, const double* G, const double* D, double* GLp,
+                       cudaStream_t st) {
+    dim3 grid(total_levels, max_chunks);
+    k_level_gram<<<grid, 256, 0, st>>>(tab_dev, G, D, GLp, g.KP * g.KP, max_chunks);
 }
 
-void launch_row_rhs(const Geom& g, bool masked, const RowDesign& d, const double* B, const double* G, const double* D, const double* U,
-                    double* T, cudaStream_t st) {
-    k_row_rhs<<<(g.N + 7) / 8, 256, 0, st>>>(g.N, g.KP, d.level_of_row, d.A, B, G, masked ? D : nullptr, U, T);
-}
-
-void launch_level_solve(const Geom& g, bool masked, const RowDesign& d, const double* G, const double* GL, const double* T, double lambda,
-                        double* U, int* err_flag, cudaStream_t st) {
+void launch_level_factor(const Geom& g, bool masked, const LevelTable* tab_dev, int total_levels, int max_chunks, const double* G,
+                         const double* GLp, double lambda, double* Lfac, int* err_flag, cudaStream_t st) {
     const size_t smem = (size_t)g.KP * (g.KP + 1) * 8;
-    k_level_solve<<<d.L, 32, smem, st>>>(g.K, g.KP, masked ? 1 : 0, d.rows_sorted, d.level_start, d.A, G, GL, T, lambda, U, err_flag);
+    k_level_factor<<<total_levels, 32, smem, st>>>(tab_dev, g.K, g.KP, masked ? 1 : 0, G, GLp, max_chunks, lambda, Lfac, err_flag);
+}
+
+void launch_row_rhs(const Geom& g, const RowDesign& d, const double* B, const double* G, const double* D, const double* U, double* T,
+                    cudaStream_t st) {
+    k_row_rhs<<<(g.N + 7) / 8, 256, 0, st>>>(g.N, g.KP, d.level_of_row, d.A, B, G, D, U, T);
+}
+
+void launch_level_update(const Geom& g, bool masked, const RowDesign& d, int lfac_base, const double* G, const double* B, const double* T,
+                         const double* Lfac, double* U, cudaStream_t st) {
+    k_level_update<<<d.L, 128, 0, st>>>(g.K, g.KP, masked ? 1 : 0, d.rows_sorted, d.level_start, d.A, G, B, T, Lfac, lfac_base, U);
 }
 
 size_t continuous_scratch_elems(const Geom& g) { return (size_t)((g.N + 63) / 64) * (g.KP * g.KP + g.KP); }
@@ -248,10 +343,15 @@ void launch_continuous(const Geom& g, bool masked, const double* x, double* w, c
     k_cont_final<<<1, 256, smem, st>>>(g.N, g.K, g.KP, masked ? 1 : 0, n_chunks, x, scratch, lambda, w, U, err_flag);
 }
 
+int build_u_parts(const Geom& g) { return (g.N + 31) / 32; }
+
 void launch_build_u(const Geom& g, int C, const RowDesign* designs_dev, int Q, const double* X, const double* W, double* U, double* Ut,
-                    cudaStream_t st) {
-    const int64_t n = (int64_t)g.N * g.KP;
-    k_build_u<<<(int)((n + 255) / 256), 256, 0, st>>>(g.N, g.KP, g.ldT, C, designs_dev, Q, X, W, U, Ut);
+                    double* UtU, cudaStream_t st) {
+    // UtU buffer: [KP*KP] result followed by build_u_parts(g) partial blocks
+    const int n_parts = build_u_parts(g);
+    double* parts = UtU + (size_t)g.KP * g.KP;
+    k_build_u<<<n_parts, 256, 0, st>>>(g.N, g.KP, g.ldT, C, designs_dev, Q, X, W, U, Ut, parts);
+    k_gram_u_final<<<(g.KP * g.KP + 255) / 256, 256, 0, st>>>(parts, UtU, n_parts, g.KP * g.KP);
 }
 
 }  // namespace ib

@@ -44,8 +44,6 @@ void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, d
 // fixed-order reductions of the partial buffers:
 //   B[N][K] = sum_s Bp[s] ; G[KP*KP] = sum_b Gp[b] ; D[N][KP*KP] = sum_s Dp[s]
 void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st);
-// UtU[KP*KP] = U^T U   (single block; U is N x KP row-major)
-void launch_gram_u(const Geom& g, const double* U, double* UtU, cudaStream_t st);
 
 // ---- row side (k_rows.cu) -----------------------------------------------------------------------------------
 struct RowDesign {            // one categorical confounder
@@ -55,21 +53,30 @@ struct RowDesign {            // one categorical confounder
     const int* level_start;   // [L+1]
     double* A;                // [L][KP] row-major factor
 };
-// Gk_c_s[L][KP*KP] = sum_{k in s} (G - D_k)   (masked path; once per iteration per confounder)
-void launch_level_gram(const Geom& g, const RowDesign& d, const double* G, const double* D, double* GL, cudaStream_t st);
-// T[k][:] = B_k - Gk_k (u_k - a_{c,z(k)})   (masked) or  B_k - G (u_k - a)   (dense)
-void launch_row_rhs(const Geom& g, bool masked, const RowDesign& d, const double* B, const double* G, const double* D, const double* U,
-                    double* T, cudaStream_t st);
-// per level: solve (XtX + lambda I) a = sum_{k in s} T_k ; XtX = GL[s] (masked) or n_s G (dense); update A and the rows of U
-void launch_level_solve(const Geom& g, bool masked, const RowDesign& d, const double* G, const double* GL, const double* T, double lambda,
-                        double* U, int* err_flag, cudaStream_t st);
+struct LevelTable {           // one level of one confounder (all confounders concatenated)
+    const int* rows_sorted;   // the confounder's rows grouped by level
+    int row_begin, row_end;   // this level's slice of rows_sorted
+};
+// masked path: GLp[level][chunk][KP*KP] = sum over 32-row chunks of (G - D_k)   (all levels of all confounders, one launch)
+void launch_level_gram(const Geom& g, const LevelTable* tab_dev, int total_levels, int max_chunks, const double* G, const double* D, double* GLp,
+                       cudaStream_t st);
+// batched K x K Cholesky, one warp per level: XtX_s = sum_chunks GLp (masked) or n_s G (dense), + lambda I -> Lfac[level][KP*KP + KP]
+void launch_level_factor(const Geom& g, bool masked, const LevelTable* tab_dev, int total_levels, int max_chunks, const double* G,
+                         const double* GLp, double lambda, double* Lfac, int* err_flag, cudaStream_t st);
+// masked path: T[k][:] = B_k - (G - D_k)(u_k - a_{c,z(k)})
+void launch_row_rhs(const Geom& g, const RowDesign& d, const double* B, const double* G, const double* D, const double* U, double* T,
+                    cudaStream_t st);
+// per level of confounder d: right-hand side, substitution with the stored factor, update A and the rows of U
+void launch_level_update(const Geom& g, bool masked, const RowDesign& d, int lfac_base, const double* G, const double* B, const double* T,
+                         const double* Lfac, double* U, cudaStream_t st);
 // continuous covariate q: H = sum_k x_k^2 Gk_k, Tq = sum_k x_k (B_k - Gk_k u_k); cyclic coordinate update / solve; updates w and U
 void launch_continuous(const Geom& g, bool masked, const double* x, double* w /*[KP]*/, const double* B, const double* G, const double* D,
                        double lambda, double* U, double* scratch, int* err_flag, cudaStream_t st);
 size_t continuous_scratch_elems(const Geom& g);
-// U = sum_c A_c[z_c] + X W ; also writes Ut
+// U = sum_c A_c[z_c] + X W ; also writes Ut and UtU = U^T U (UtU buffer: KP*KP result + build_u_parts(g) partial blocks)
 void launch_build_u(const Geom& g, int C, const RowDesign* designs_dev, int Q, const double* X, const double* W, double* U, double* Ut,
-                    cudaStream_t st);
+                    double* UtU, cudaStream_t st);
+int build_u_parts(const Geom& g);
 
 // ---- column side (k_cd.cu) ----------------------------------------------------------------------------------
 struct CdParams {
@@ -79,13 +86,15 @@ struct CdParams {
     uint64_t seed;
     int perm_mode;
 };
-// per gene: (masked: XtX_j = UtU - sum_{i: m_ij=0} u_i u_i^T) ; alpha == 0 -> ridge solve, else elastic-net CD. Updates V in place.
-void launch_col_solve(const Geom& g, bool masked, const uint32_t* trC, const double* U, const double* UtU, const double* Xty, double* V,
-                      const CdParams& p, unsigned long long* sweeps, int* err_flag, cudaStream_t st);
-// stand-alone batched solver (insider_b200_strong_cd): XtX either shared (KP*KP) or per column [n][KP*KP]
+// masked path: XtXall[j][KP*KP] = UtU - sum_{i: m_ij=0} u_i u_i^T for every local gene (DMMA gathers, one warp per gene)
+void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, double* XtXall, cudaStream_t st);
+// per gene: alpha == 0 -> ridge solve, else elastic-net CD (persistent groups pulling genes from `queue`). Updates V in place.
+void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
+                      unsigned long long* sweeps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st);
+// stand-alone batched solver (insider_b200_strong_cd): XtX column-major K x K, either shared or per column [n][K*K]
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,
-                     cudaStream_t st);
+                     unsigned int* queue, int sm_count, cudaStream_t st);
 
 // ---- misc (k_misc.cu) ---------------------------------------------------------------------------------------
 // src: n_genes columns of N mask elements (INSIDER_MASK_* kind) -> dstC[n_genes][Wp] bit-packed
@@ -104,7 +113,7 @@ struct CheckState {           // device-resident loop state
 // reduce the SSE partials (fixed order) into state->{sse_train, sse_test, v2, v1}
 void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, cudaStream_t st);
 // row_reg = lambda1 * sum ||A_c||^2 (+ W); then loss, delta, decay ladder, convergence (src/optimize.cpp:381-408)
-void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, void* record_out, cudaStream_t st);
+void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, int iter, void* record_out, cudaStream_t st);
 void launch_bump_iter(CheckState* state, cudaStream_t st);
 
 }  // namespace ib

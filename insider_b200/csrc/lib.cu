@@ -60,21 +60,22 @@ struct Err { int code; std::string msg; };
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw Err{INSIDER_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)}; } while (0)
 #define REQUIRE(c, msg) do { if (!(c)) throw Err{INSIDER_ERR_INVALID_ARG, msg}; } while (0)
 
-template <typename T> T* dalloc(size_t n) {
-    T* p = nullptr;
-    if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e != cudaSuccess) throw Err{INSIDER_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e)};
-    return p;
-}
+// Stream-ordered allocations from the device's default memory pool (release threshold raised at context creation), so
+// that the 51 back-to-back fits of tune() reuse their buffers instead of paying cudaMalloc/cudaFree every time.
 struct DevPool {                       // frees everything it handed out
     std::vector<void*> ptrs;
+    cudaStream_t stream = nullptr;
     template <typename T> T* get(size_t n, bool zero = true, cudaStream_t st = 0) {
-        T* p = dalloc<T>(n); ptrs.push_back(p);
-        if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), st);
+        if (n == 0) n = 1;
+        if (st) stream = st;
+        T* p = nullptr;
+        cudaError_t e = cudaMallocAsync((void**)&p, n * sizeof(T), stream);
+        if (e != cudaSuccess) { cudaGetLastError(); throw Err{INSIDER_ERR_NOMEM, std::string("cudaMallocAsync failed: ") + cudaGetErrorString(e)}; }
+        ptrs.push_back(p);
+        if (zero) cudaMemsetAsync(p, 0, n * sizeof(T), stream);
         return p;
     }
-    ~DevPool() { for (void* p : ptrs) cudaFree(p); }
+    ~DevPool() { for (void* p : ptrs) cudaFreeAsync(p, stream); }
 };
 
 }  // namespace
@@ -95,6 +96,7 @@ struct insider_resident {
     uint32_t *trC = nullptr, *teC = nullptr, *trR = nullptr;
     std::vector<int> L;
     std::vector<int*> level_of_row, rows_sorted, level_start;
+    std::vector<std::vector<int>> level_start_host;
     double n_train = 0, n_test = 0;
     double h2d_bytes = 0;
     DevPool pool;
@@ -115,9 +117,14 @@ struct insider_session {
     double *V = nullptr, *Xty = nullptr, *A_all = nullptr, *U = nullptr, *Ut = nullptr, *UtU = nullptr;
     double *stats = nullptr, *B = nullptr, *G = nullptr, *D = nullptr;   // stats = [B | G | D] (one all-reduce)
     size_t stats_elems = 0;
-    double *Bp = nullptr, *Gp = nullptr, *Dp = nullptr, *GL = nullptr, *T = nullptr, *cont_scratch = nullptr, *sse_part = nullptr;
+    double *Bp = nullptr, *Gp = nullptr, *Dp = nullptr, *GLp = nullptr, *T = nullptr, *cont_scratch = nullptr, *sse_part = nullptr;
+    double* XtXall = nullptr;           // masked path: per-gene Gram matrices [P_l][KP*KP]
+    unsigned int* queue = nullptr;      // gene queue of the persistent CD kernel
     double* Vfull = nullptr;            // world > 1: gathered V for the final download
-    std::vector<size_t> gl_off;
+    std::vector<int> lfac_base;         // first level-table index of each confounder
+    int total_levels = 0, max_chunks = 1;
+    LevelTable* tab_dev = nullptr;
+    double* Lfac = nullptr;             // [total_levels][KP*KP + KP] Cholesky factors + inverse diagonals
     int rb_splits = 1, gv_blocks = 1, d_splits = 1, stream_blocks = 1;
     RowDesign* designs_dev = nullptr;
     std::vector<RowDesign> designs;
@@ -133,6 +140,9 @@ struct insider_session {
     double loop_ms = 0, h2d = 0, d2h = 0;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraphExec_t iter_graph = nullptr;   // one ALS iteration (run_iteration + k_bump_iter), replayed
+    int64_t launches_per_iter = 0;
+    bool graph_failed = false;
     std::vector<ProfEntry> prof;
     std::map<std::string, std::pair<double, int64_t>> prof_acc;
     DevPool pool;
@@ -186,6 +196,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
     cudaStream_t st = ctx->stream;
     auto* r = new insider_resident();
     try {
+        r->pool.stream = st;
         r->ctx = ctx; r->N = pb->N; r->P = pb->P; r->C = pb->C; r->Q = pb->inc_continuous ? pb->Q : 0; r->inc_continuous = pb->inc_continuous;
         r->has_masks = pb->mask_kind != INSIDER_MASK_NONE;
         split_genes(r->P, ctx->world, ctx->rank, r->j0, r->Pl);
@@ -217,6 +228,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
             CUDA_TRY(cudaMemcpyAsync(d_sorted, sorted.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d_start, start.data(), (L + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
+            r->level_start_host.push_back(start);
             r->L.push_back(L); r->level_of_row.push_back(d_lor); r->rows_sorted.push_back(d_sorted); r->level_start.push_back(d_start);
             r->h2d_bytes += (2.0 * N + L + 1) * 4;
         }
@@ -234,7 +246,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
             const size_t esz = pb->mask_kind == INSIDER_MASK_INT32 ? 4 : pb->mask_kind == INSIDER_MASK_UINT8 ? 1 : 8;
             const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(r->Pl, (int64_t)((size_t)512 << 20) / (esz * N)));
             void* tmp = nullptr;
-            CUDA_TRY(cudaMalloc(&tmp, (size_t)chunk * N * esz));
+            CUDA_TRY(cudaMallocAsync(&tmp, (size_t)chunk * N * esz, st));
             try {
                 for (int pass = 0; pass < 2; ++pass) {
                     const char* src = (const char*)(pass == 0 ? pb->train : pb->test);
@@ -254,8 +266,8 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
                 CUDA_TRY(cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
                 r->n_train = (double)h[0]; r->n_test = (double)h[1];
-            } catch (...) { cudaFree(tmp); throw; }
-            cudaFree(tmp);
+            } catch (...) { cudaFreeAsync(tmp, st); throw; }
+            cudaFreeAsync(tmp, st);
             if (ctx->world > 1) {
                 double* d2 = r->pool.get<double>(2, false);
                 double hv[2] = {r->n_train, r->n_test};
@@ -324,7 +336,7 @@ void evaluate(insider_session* s, bool initial) {
     { Launch l(s, "k_sse_reduce"); launch_sse_reduce(s->sse_part, s->stream_blocks, s->state, st); }
     if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(&s->state->sse_train, &s->state->sse_train, 4, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(sse)");
     insider_check* rec = s->records_dev + std::min(s->n_records, s->max_records - 1);
-    { Launch l(s, "k_check"); launch_check(s->state, s->A_all, (int64_t)s->n_A, initial ? 1 : 0, rec, st); }
+    { Launch l(s, "k_check"); launch_check(s->state, s->A_all, (int64_t)s->n_A, initial ? 1 : 0, (int)s->iter, rec, st); }
     struct { insider_check rec; } hostrec;
     CheckState hs;
     CUDA_TRY(cudaMemcpyAsync(&hostrec.rec, rec, sizeof(insider_check), cudaMemcpyDeviceToHost, st));
@@ -368,12 +380,16 @@ void run_iteration(insider_session* s) {
         { Launch l(s, "k_reduce"); launch_reduce_partials(s->D, s->Dp, (int64_t)g.N * KK, s->d_splits, st); }
     }
     if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->stats, s->stats, s->stats_elems, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(stats)");
+    // normal-equation matrices of every level of every confounder: assembled and factorised once (they do not depend on A)
+    if (r->C > 0) {
+        if (s->masked) { Launch l(s, "k_level_gram"); launch_level_gram(g, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->D, s->GLp, st); }
+        { Launch l(s, "k_level_factor"); launch_level_factor(g, s->masked, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, st); }
+    }
     // Gauss-Seidel over confounder blocks (:335-362)
     for (int c = 0; c < r->C; ++c) {
         const RowDesign& d = s->designs[c];
-        if (s->masked) { Launch l(s, "k_level_gram"); launch_level_gram(g, d, s->G, s->D, s->GL + s->gl_off[c], st); }
-        { Launch l(s, "k_row_rhs"); launch_row_rhs(g, s->masked, d, s->B, s->G, s->D, s->U, s->T, st); }
-        { Launch l(s, "k_level_solve"); launch_level_solve(g, s->masked, d, s->G, s->GL + s->gl_off[c], s->T, s->opt.lambda1, s->U, s->err_dev, st); }
+        if (s->masked) { Launch l(s, "k_row_rhs"); launch_row_rhs(g, d, s->B, s->G, s->D, s->U, s->T, st); }
+        { Launch l(s, "k_level_update"); launch_level_update(g, s->masked, d, s->lfac_base[c], s->G, s->B, s->T, s->Lfac, s->U, st); }
     }
     if (r->inc_continuous) {
         double* W = s->A_all + s->a_off[r->C];
@@ -383,11 +399,11 @@ void run_iteration(insider_session* s) {
         }
     }
     // row factor rebuild (:365-373) and column update (:376)
-    { Launch l(s, "k_build_u"); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, st); }
-    { Launch l(s, "k_gram_u", 2); launch_gram_u(g, s->U, s->UtU, st); }
+    { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
-    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, r->trC, s->U, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->err_dev, st); }
+    if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
+    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->queue, s->err_dev, s->ctx->sm_count, st); }
 }
 
 insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* f, const insider_options* o) {
@@ -405,6 +421,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
     cudaStream_t st = ctx->stream;
     auto* s = new insider_session();
     try {
+        s->pool.stream = st;
         s->ctx = ctx; s->r = r; s->opt = *o;
         if (s->opt.check_every == 0) s->opt.check_every = 10;
         if (s->opt.perm_mode == 0) s->opt.perm_mode = INSIDER_PERM_COUNTER;
@@ -424,7 +441,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->A_all = s->pool.get<double>(s->n_A, true, st);
         s->U = s->pool.get<double>((size_t)g.N * g.KP, true, st);
         s->Ut = s->pool.get<double>((size_t)g.KP * g.ldT + 64, true, st);
-        s->UtU = s->pool.get<double>((size_t)KK * (1 + (g.N + 255) / 256), true, st);
+        s->UtU = s->pool.get<double>((size_t)KK * (1 + build_u_parts(g)), true, st);
         s->stats_elems = (size_t)g.N * g.KP + KK + (s->masked ? (size_t)g.N * KK : 0);
         s->stats = s->pool.get<double>(s->stats_elems, true, st);
         s->B = s->stats; s->G = s->B + (size_t)g.N * g.KP; s->D = s->masked ? s->G + KK : nullptr;
@@ -435,16 +452,31 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->stream_blocks = stream_default_blocks(g, ctx->sm_count);
         s->sse_part = s->pool.get<double>((size_t)s->stream_blocks * 4, true, st);
         s->T = s->pool.get<double>((size_t)g.N * g.KP, true, st);
+        // level table over all confounders
+        {
+            std::vector<LevelTable> tab;
+            for (int c = 0; c < r->C; ++c) {
+                s->lfac_base.push_back((int)tab.size());
+                for (int l = 0; l < r->L[c]; ++l) {
+                    const int b = r->level_start_host[c][l], e = r->level_start_host[c][l + 1];
+                    tab.push_back(LevelTable{r->rows_sorted[c], b, e});
+                    s->max_chunks = std::max(s->max_chunks, (e - b + 31) / 32);
+                }
+            }
+            s->total_levels = (int)tab.size();
+            s->tab_dev = s->pool.get<LevelTable>(std::max<size_t>(1, tab.size()), true, st);
+            if (!tab.empty()) CUDA_TRY(cudaMemcpyAsync(s->tab_dev, tab.data(), tab.size() * sizeof(LevelTable), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            s->Lfac = s->pool.get<double>((size_t)std::max(1, s->total_levels) * (KK + g.KP), true, st);
+        }
         if (s->masked) {
             s->d_splits = std::max(1, std::min(16, (ctx->sm_count * 16 + g.N - 1) / g.N));
             s->d_splits = std::min(s->d_splits, std::max(1, g.WPr));
             s->Dp = s->pool.get<double>((size_t)s->d_splits * g.N * KK, true, st);
-            size_t go = 0;
-            for (int c = 0; c < r->C; ++c) { s->gl_off.push_back(go); go += (size_t)r->L[c] * KK; }
-            s->GL = s->pool.get<double>(go, true, st);
+            s->GLp = s->pool.get<double>((size_t)std::max(1, s->total_levels) * s->max_chunks * KK, true, st);
+            s->XtXall = s->pool.get<double>((size_t)std::max<int64_t>(1, g.P) * KK, true, st);
         } else {
-            for (int c = 0; c < r->C; ++c) s->gl_off.push_back(0);
-            s->GL = s->pool.get<double>(1, true, st);
+            s->GLp = s->pool.get<double>(1, true, st);
         }
         if (r->inc_continuous) s->cont_scratch = s->pool.get<double>(continuous_scratch_elems(g), true, st);
         if (ctx->world > 1) s->Vfull = s->pool.get<double>((size_t)r->P * g.ldV, true, st);
@@ -460,14 +492,48 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->max_records = (uint32_t)std::min<uint64_t>((uint64_t)o->max_iter / s->opt.check_every + 3, 1u << 20);
         s->records_dev = s->pool.get<insider_check>(s->max_records, true, st);
         s->sweeps_dev = s->pool.get<unsigned long long>(1, true, st);
+        s->queue = s->pool.get<unsigned int>(1, true, st);
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
         upload_factors(s, f);
         // initial row factor and evaluation (:286-289, :320-323)
-        { Launch l(s, "k_build_u"); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, st); }
+        { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
         evaluate(s, true);
     } catch (...) { if (s->ev0) cudaEventDestroy(s->ev0); if (s->ev1) cudaEventDestroy(s->ev1); delete s; throw; }
     return s;
+}
+
+// one iteration + iteration-counter bump, replayed as a CUDA graph unless per-kernel profiling is on
+void launch_iteration(insider_session* s) {
+    cudaStream_t st = s->ctx->stream;
+    const bool want_graph = s->opt.use_graph >= 0 && !s->ctx->profile && !s->graph_failed;
+    if (!want_graph) {
+        run_iteration(s);
+        { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
+        return;
+    }
+    if (!s->iter_graph) {
+        const int64_t before = s->launches;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        try {
+            run_iteration(s);
+            launch_bump_iter(s->state, st); s->launches += 1;
+        } catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        s->launches_per_iter = s->launches - before;
+        s->launches = before;
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&s->iter_graph, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {                       // fall back to plain launches (still the CUDA path)
+            cudaGetLastError(); s->iter_graph = nullptr; s->graph_failed = true;
+            run_iteration(s);
+            { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
+            return;
+        }
+    }
+    CUDA_TRY(cudaGraphLaunch(s->iter_graph, st));
+    s->launches += s->launches_per_iter;
 }
 
 void do_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms) {
@@ -477,10 +543,11 @@ void do_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms) {
     uint32_t ran = 0;
     while (!s->done && ran < n_iters) {
         if (s->iter > s->opt.max_iter) { s->done = true; break; }                  // while(iter <= max_iter)  :325
-        run_iteration(s);
+        // the device-side iteration counter (permutation keys) is bumped at the end of the iteration; the evaluation of a
+        // check iteration therefore receives the iteration index from the host
+        launch_iteration(s);
         if (s->iter % s->opt.check_every == 0) evaluate(s, false);                 // :381
         if (s->done) break;                                                        // :405-407 (iter not incremented on break)
-        { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
         s->iter++; ran++;                                                          // :409
         if (s->iter > s->opt.max_iter) s->done = true;
     }
@@ -510,6 +577,7 @@ void fill_result(insider_session* s, insider_result* res) {
 void destroy_session(insider_session* s) {
     if (!s) return;
     for (auto& p : s->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    if (s->iter_graph) cudaGraphExecDestroy(s->iter_graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -537,6 +605,10 @@ int create_ctx(insider_ctx** out, int device, int rank, int world, const void* i
         c->device = device; c->sm_count = prop.multiProcessorCount; c->rank = rank; c->world = world;
         try {
             CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            {
+                cudaMemPool_t mp = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) { uint64_t thr = UINT64_MAX; cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr); }
+            }
             if (world > 1) {
                 std::string err;
                 if (!g_nccl.load(err)) throw Err{INSIDER_ERR_NCCL, err};
@@ -675,15 +747,16 @@ int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const do
         if (n_cols == 0) return;
         CUDA_TRY(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
-        DevPool pool;
+        DevPool pool; pool.stream = st;
         const size_t gsz = (size_t)K * K * (shared_gram ? 1 : n_cols);
         double* dG = pool.get<double>(gsz, false); double* dx = pool.get<double>((size_t)K * n_cols, false);
         double* dw = pool.get<double>((size_t)K * n_cols, false); double* db = pool.get<double>((size_t)K * n_cols, true, st);
         int* dsw = pool.get<int>(n_cols, true, st);
+        unsigned int* dq = pool.get<unsigned int>(1, true, st);
         CUDA_TRY(cudaMemcpyAsync(dG, XtX, gsz * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dx, Xty, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dw, wstart, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
-        launch_cd_batch(K, n_cols, dG, shared_gram != 0, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, st);
+        launch_cd_batch(K, n_cols, dG, shared_gram != 0, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, dq, ctx->sm_count, st);
         CUDA_TRY(cudaMemcpyAsync(beta, db, (size_t)K * n_cols * 8, cudaMemcpyDeviceToHost, st));
         if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, (size_t)n_cols * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -722,10 +795,11 @@ int insider_b200_fit_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t
             if (s->masked) {
                 launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st);
                 launch_reduce_partials(s->D, s->Dp, (int64_t)g.N * KK, s->d_splits, st);
-                launch_level_gram(g, s->designs[0], s->G, s->D, s->GL, st);
+                launch_level_gram(g, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->D, s->GLp, st);
+                launch_row_rhs(g, s->designs[0], s->B, s->G, s->D, s->U, s->T, st);
             }
-            launch_row_rhs(g, s->masked, s->designs[0], s->B, s->G, s->D, s->U, s->T, st);
-            launch_level_solve(g, s->masked, s->designs[0], s->G, s->GL, s->T, 0.0, s->U, s->err_dev, st);
+            launch_level_factor(g, s->masked, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, 0.0, s->Lfac, s->err_dev, st);
+            launch_level_update(g, s->masked, s->designs[0], 0, s->G, s->B, s->T, s->Lfac, s->U, st);
             CUDA_TRY(cudaStreamSynchronize(st));
             download_factors(s, &f);
             int err = 0; CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));

@@ -48,6 +48,26 @@ def main():
         if profile:
             for k, (ms, calls) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
                 print(f"  {k:20s} {ms:10.3f} ms  {calls:6d} calls  {1e3 * ms / calls:9.1f} us/call")
+    long_iters = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+    if long_iters:
+        for profile in (False, True):
+            ctx.set_profile(profile)
+            fac = _cabi.HostFactors(F0, V0, K)
+            s = res.begin(fac, opt)
+            s.step(long_iters)
+            if profile:
+                s.profile()   # discard: only the tail is of interest
+            p0 = s.profile()
+            sw0 = 0
+            done, ms = s.step(20)
+            p1 = s.profile()
+            out = s.end()
+            print(f"late phase (iterations {long_iters}..{long_iters + 19}) profile={profile}: {ms / 20:.3f} ms/iter; total sweeps so far {out['cd_sweeps']}; loss {out['loss']:.9g}; checks decay {[c['decay'] for c in out['checks']][-3:]}")
+            if profile:
+                for k in sorted(p1, key=lambda k: -(p1[k][0] - p0.get(k, (0, 0))[0])):
+                    dms = p1[k][0] - p0.get(k, (0, 0))[0]; dc = p1[k][1] - p0.get(k, (0, 0))[1]
+                    if dc:
+                        print(f"  {k:20s} {dms:10.3f} ms  {dc:6d} calls  {1e3 * dms / dc:9.1f} us/call")
 
 
 if __name__ == "__main__":

@@ -194,6 +194,16 @@ def run_ours(args, w, rank, world, local):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = args.steps / t_e2e
 
+    # ---- steady-state iterations (late phase of the fit: a few sweeps per gene); every rank takes part
+    ms_late = None
+    if not args.no_late:
+        sl = res.begin(_cabi.HostFactors(F0, V0, K), opts(10 ** 6))
+        sl.step(args.late_start)
+        barrier()
+        _, ms_late = sl.step(20)
+        sl.end(read_factors=False)
+        ms_late = max_over_ranks(ms_late)
+
     if rank == 0:
         peaks = {}
         try:
@@ -218,13 +228,35 @@ def run_ours(args, w, rank, world, local):
             if kname in kern:
                 stream[kname] = {"algorithmic_bytes": y_bytes, "GBps": y_bytes / (kern[kname]["us_per_call"] * 1e-6) / 1e9,
                                  "frac_of_hbm_peak": y_bytes / (kern[kname]["us_per_call"] * 1e-6) / 1e9 / hbm_peak}
+        # dominant kernel: the persistent elastic-net solver. Algorithmic FP64 flops per coordinate update: 2K for the
+        # q -= delta * XtX[:,k] update + 12 for the soft-threshold / exact division / loss-decrement chain.
+        FP64_PEAK = 37.1   # TFLOP/s, measured on this pool by tools/microbench.cu (profiles/r01_microbench_fp64_hbm.txt)
         cd = None
         if "k_col_solve" in kern:
-            sweeps = outp["cd_sweeps"]
-            cd = {"gene_sweeps": sweeps, "gene_sweeps_per_s": sweeps / (kern["k_col_solve"]["ms_total"] * 1e-3),
-                  "flops_per_gene_sweep_upper": 2 * K * K + 12 * K,
-                  "fp64_tflops_upper": sweeps * (2 * K * K + 12 * K) / (kern["k_col_solve"]["ms_total"] * 1e-3) / 1e12,
-                  "fp64_peak_tflops_measured": 37.1}
+            steps_cd, sweeps = outp["cd_steps"], outp["cd_sweeps"]
+            secs = kern["k_col_solve"]["ms_total"] * 1e-3
+            flops = steps_cd * (2.0 * K + 12.0)
+            cd = {"gene_sweeps": sweeps, "coordinate_updates": steps_cd, "gene_sweeps_per_s": sweeps / secs,
+                  "algorithmic_flops": flops, "fp64_tflops": flops / secs / 1e12, "fp64_peak_tflops_measured": FP64_PEAK,
+                  "share_of_iteration": kern["k_col_solve"]["share"]}
+        roof_dom = None
+        if cd:
+            roof_dom = {"bound": "tensor", "kernel": "k_cd_persistent (launched as k_col_solve)", "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
+                        "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": None,
+                        "peak_source": "FP64 pipe peak measured with DMMA m8n8k4 by tools/microbench.cu on this pool's B200 (MEASURED_PEAKS.json has "
+                                       "no FP64 entry; its bf16 tensor peak does not apply to an FP64 path)",
+                        "note": "sequential coordinate descent on K=23 vectors: bound by instruction issue / FP64 latency chains, not by a "
+                                "throughput roof; issue-slot utilisation and stall reasons are in profiles/r01_ncu_k_cd_persistent_*.txt",
+                        "algorithmic_flops_per_launch": flops / max(1, kern["k_col_solve"]["calls"]),
+                        "avg_launch_ms": kern["k_col_solve"]["ms_total"] / max(1, kern["k_col_solve"]["calls"])}
+        roof_iter = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_iteration": b_iter,
+                     "what": "whole ALS iteration, SURVEY.md 8(d) bytes / mean iteration time (per GPU)", "dominant_kernel": dominant}
+        # steady-state iterations (late phase of the fit: a few sweeps per gene), for context
+        late = None
+        if ms_late is not None:
+            late = {"iterations": f"{args.late_start}..{args.late_start + 19}", "ms_per_iteration": ms_late / 20,
+                    "hbm_GBps_algorithmic": b_iter / (ms_late / 20 * 1e-3) / 1e9 / world, "frac_of_hbm_peak": b_iter / (ms_late / 20 * 1e-3) / 1e9 / world / hbm_peak}
         line = {
             "metric": "als_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -236,10 +268,10 @@ def run_ours(args, w, rank, world, local):
                     "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y"},
             "gpu_launches": int(out["kernel_launches"]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_iteration": b_iter,
-                         "what": "whole ALS iteration, SURVEY.md 8(d) bytes / mean iteration time (per GPU)", "dominant_kernel": dominant},
+            "roofline": roof_dom or roof_iter,
+            "roofline_iteration_hbm": roof_iter,
             "roofline_kernels": {"streaming": stream, "coordinate_descent": cd, "kernels": kern, "profiled_iterations": n_prof},
+            "late_phase": late,
             "cd_sweeps_per_gene_iter": out["cd_sweeps"] / max(1, Pl) / args.steps,
             "loss_after_timed": out["loss"], "wall_s_timed_region": t_wall,
         }
@@ -271,6 +303,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ageing_full_377x44477_K23_fit", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-late", action="store_true", help="skip the steady-state (late iterations) measurement")
+    ap.add_argument("--late-start", type=int, default=150)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     w = WORKLOADS[args.workload]

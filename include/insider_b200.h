@@ -122,6 +122,7 @@ typedef struct {
     double loop_ms;                     /* device time of the ALS loop (CUDA events on the library's stream) */
     double h2d_bytes, d2h_bytes;        /* bytes copied by this call */
     int64_t kernel_launches;            /* kernels launched by this call */
+    int64_t cd_steps;                   /* total coordinate updates attempted by the elastic-net solver (statistics) */
 } insider_result;
 
 void insider_b200_default_options(insider_options* opt);

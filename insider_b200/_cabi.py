@@ -58,7 +58,7 @@ class Check(C.Structure):
 class Result(C.Structure):
     _fields_ = [("train_rmse", C.c_double), ("test_rmse", C.c_double), ("loss", C.c_double), ("iters_run", C.c_uint32),
                 ("n_checks", C.c_uint32), ("checks", C.POINTER(Check)), ("max_checks", C.c_uint32), ("cd_sweeps", C.c_int64),
-                ("loop_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("kernel_launches", C.c_int64)]
+                ("loop_ms", C.c_double), ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double), ("kernel_launches", C.c_int64), ("cd_steps", C.c_int64)]
 
 
 _lib = None
@@ -164,7 +164,7 @@ def make_result(max_checks: int):
 def result_dict(r: Result, buf) -> dict:
     checks = [{k: getattr(buf[i], k) for k, _ in Check._fields_ if k != "pad"} for i in range(r.n_checks)]
     return dict(train_rmse=r.train_rmse, test_rmse=r.test_rmse, loss=r.loss, iters_run=r.iters_run, checks=checks, cd_sweeps=r.cd_sweeps,
-                loop_ms=r.loop_ms, h2d_bytes=r.h2d_bytes, d2h_bytes=r.d2h_bytes, kernel_launches=r.kernel_launches)
+                loop_ms=r.loop_ms, h2d_bytes=r.h2d_bytes, d2h_bytes=r.d2h_bytes, kernel_launches=r.kernel_launches, cd_steps=r.cd_steps)
 
 
 class Context:

@@ -153,7 +153,7 @@ struct CdArgs {
     const double* tol_dev; double tol_host;
     const uint32_t* als_iter_dev; uint32_t als_iter_host;
     uint64_t seed; int perm_mode;
-    unsigned long long* sweeps_total; int* sweeps_per_gene;
+    unsigned long long* sweeps_total; unsigned long long* steps_total; int* sweeps_per_gene;
     unsigned int* queue;          // atomic gene counter (zeroed before launch)
 };
 
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     bool active = false, retired = false;
     uint32_t inc = 0, draw = 0;
     int n_inc = 0, sweeps = 0;
-    unsigned long long sweeps_acc = 0;
+    unsigned long long sweeps_acc = 0, steps_acc = 0;
 
     while (true) {
         // ---- claim and set up a new gene (divergent per group; group-local masks only)
@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
         if (active) {
             ++sweeps;
+            steps_acc += (unsigned long long)n_on;      // coordinate updates attempted (statistics only)
             if (inner_end) {
                 if (vmask == 0u || sweeps >= MAX_SWEEPS) {
                     // finished: write the gene back (coordinate layout)
@@ -373,6 +374,9 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     // one atomic per warp for the sweep statistics
     sweeps_acc += __shfl_xor_sync(FULL, sweeps_acc, 8); sweeps_acc += __shfl_xor_sync(FULL, sweeps_acc, 16);
     if (lane == 0 && sweeps_acc && a.sweeps_total) atomicAdd(a.sweeps_total, sweeps_acc);
+    if (li != 0) steps_acc = 0;
+    steps_acc += __shfl_xor_sync(FULL, steps_acc, 8); steps_acc += __shfl_xor_sync(FULL, steps_acc, 16);
+    if (lane == 0 && steps_acc && a.steps_total) atomicAdd(a.steps_total, steps_acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -457,7 +461,7 @@ void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const 
 }
 
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
-                      unsigned long long* sweeps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st) {
+                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st) {
     if (g.P == 0) return;
     if (p.alpha == 0.0) {
         RidgeArgs r{UtU, XtXall, Xty, V, g.K, g.KP, g.ldV, g.P, p.lambda, err_flag};
@@ -471,7 +475,7 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
     a.Xsh = UtU; a.Xall = XtXall; a.x_stride = (int64_t)g.KP * g.KP; a.xs_r = g.KP; a.xs_c = 1;
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P; a.gene0 = g.gene0;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
-    a.sweeps_total = sweeps; a.sweeps_per_gene = nullptr; a.queue = queue;
+    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = nullptr; a.queue = queue;
     launch_cd(a, g.KP, masked, sm_count, st);
 }
 
@@ -482,7 +486,7 @@ void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const dou
     a.Xsh = XtX; a.Xall = XtX; a.x_stride = (int64_t)K * K; a.xs_r = 1; a.xs_c = K;      // caller's column-major K x K
     a.Xty = Xty; a.W0 = w0; a.Vout = beta; a.ldv = K; a.K = K; a.P = n; a.gene0 = (int64_t)gene0;
     a.lambda = lambda; a.alpha = alpha; a.tol_dev = nullptr; a.tol_host = tol; a.als_iter_dev = nullptr; a.als_iter_host = als_iter;
-    a.seed = seed; a.perm_mode = perm_mode; a.sweeps_total = nullptr; a.sweeps_per_gene = sweeps; a.queue = queue;
+    a.seed = seed; a.perm_mode = perm_mode; a.sweeps_total = nullptr; a.steps_total = nullptr; a.sweeps_per_gene = sweeps; a.queue = queue;
     launch_cd(a, round_up(K, 8), !shared, sm_count, st);
 }
 

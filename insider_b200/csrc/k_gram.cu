@@ -1,6 +1,6 @@
 // Gram matrices and fixed-order reductions.
 //
-//   k_gram_v         gram = V V^T                                   src/optimize.cpp:332
+//   (gram = V V^T, src/optimize.cpp:332, is accumulated inside k_row_b: k_stream.cu)
 //   k_row_comp_gram  per-row complement  sum_{j: m_ij=0} v_j v_j^T  src/optimize.cpp:163,170 (c_factor.cols(zero_idx) * trans(..))
 //   k_reduce         deterministic sum of per-block partial buffers
 #include "common.cuh"
@@ -9,37 +9,6 @@
 namespace ib {
 
 namespace {
-
-__global__ void __launch_bounds__(256) k_gram_v(const double* __restrict__ V, double* __restrict__ Gp, int KP, int ldV, int64_t P_pad,
-                                                int n_blocks) {
-    extern __shared__ double vs[];                 // [GT][ldV]
-    constexpr int GT = 64;
-    const int tid = threadIdx.x;
-    const int64_t per = (P_pad + n_blocks - 1) / n_blocks;
-    const int64_t j0 = (int64_t)blockIdx.x * per, j1 = min(P_pad, j0 + per);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t jb = j0; jb < j1; jb += GT) {
-        const int n = (int)min((int64_t)GT, j1 - jb);
-        __syncthreads();
-        for (int x = tid; x < n * ldV; x += 256) vs[x] = V[jb * ldV + x];
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int e = tid + 256 * r;
-            if (e < KP * KP) {
-                const int a = e / KP, b = e % KP;
-                double s = acc[r];
-                for (int j = 0; j < n; ++j) s = fma(vs[j * ldV + a], vs[j * ldV + b], s);
-                acc[r] = s;
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int e = tid + 256 * r;
-        if (e < KP * KP) Gp[(size_t)blockIdx.x * KP * KP + e] = acc[r];
-    }
-}
 
 // warp per (row, split): DMMA rank-4 updates over the genes whose train bit is 0
 template <int NT>
@@ -102,20 +71,56 @@ __global__ void __launch_bounds__(256) k_row_comp_gram(const uint32_t* __restric
             }
 }
 
-__global__ void __launch_bounds__(256) k_reduce(double* __restrict__ out, const double* __restrict__ parts, int64_t n, int n_parts) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+// Fixed-order reduction of per-block partial buffers, up to three jobs per launch (B, G, D). A block owns 32 consecutive
+// elements; its 8 warps each sum every 8th partial (the loads of one warp are coalesced and independent), then the 8
+// warp sums are combined in ascending order: deterministic, and short dependency chains even for hundreds of partials.
+struct ReduceJobs { double* out[3]; const double* parts[3]; long long n[3]; int n_parts[3]; int flat[3]; int first_block[4]; };
+__global__ void __launch_bounds__(256) k_reduce(ReduceJobs jobs) {
+    __shared__ double sm[8][33];
+    int j = 0;
+    while (j < 2 && (int)blockIdx.x >= jobs.first_block[j + 1]) ++j;
+    const long long n = jobs.n[j];
+    const int np = jobs.n_parts[j];
+    if (jobs.flat[j]) {
+        // few partials: one thread per element, 256 elements per block
+        const long long i = ((long long)blockIdx.x - jobs.first_block[j]) * 256 + threadIdx.x;
+        if (i >= n) return;
+        const double* p = jobs.parts[j] + i;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int q = 0;
+        for (; q + 4 <= np; q += 4) {
+            const double v0 = p[(size_t)q * n], v1 = p[(size_t)(q + 1) * n], v2 = p[(size_t)(q + 2) * n], v3 = p[(size_t)(q + 3) * n];
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; q < np; ++q) s0 += p[(size_t)q * n];
+        jobs.out[j][i] = (s0 + s1) + (s2 + s3);
+        return;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i = ((long long)blockIdx.x - jobs.first_block[j]) * 32 + lane;
     double s = 0.0;
-    for (int p = 0; p < n_parts; ++p) s += parts[(size_t)p * n + i];
-    out[i] = s;
+    if (i < n) {
+        const double* p = jobs.parts[j] + i;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        int q = w;
+        for (; q + 24 < np; q += 32) {
+            const double v0 = p[(size_t)q * n], v1 = p[(size_t)(q + 8) * n], v2 = p[(size_t)(q + 16) * n], v3 = p[(size_t)(q + 24) * n];
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; q < np; q += 8) s0 += p[(size_t)q * n];
+        s = (s0 + s1) + (s2 + s3);
+    }
+    sm[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && i < n) {
+        double t = sm[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += sm[k][lane];
+        jobs.out[j][i] = t;
+    }
 }
 
 }  // namespace
-
-void launch_gram_v(const Geom& g, const double* V, double* Gp, int n_blocks, cudaStream_t st) {
-    const size_t smem = (size_t)64 * g.ldV * 8;
-    k_gram_v<<<n_blocks, 256, smem, st>>>(V, Gp, g.KP, g.ldV, g.P_pad, n_blocks);
-}
 
 void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, double* Dp, int n_splits, cudaStream_t st) {
     const int64_t warps = (int64_t)g.N * n_splits;
@@ -128,9 +133,25 @@ void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, d
     }
 }
 
+void launch_reduce_jobs(int n_jobs, double* const* out, const double* const* parts, const int64_t* n_elems, const int* n_parts, cudaStream_t st) {
+    ReduceJobs jobs{};
+    int blocks = 0;
+    for (int j = 0; j < 3; ++j) {
+        jobs.first_block[j] = blocks;
+        if (j < n_jobs) {
+            jobs.out[j] = out[j]; jobs.parts[j] = parts[j]; jobs.n[j] = n_elems[j]; jobs.n_parts[j] = n_parts[j];
+            jobs.flat[j] = n_parts[j] < 32 ? 1 : 0;
+            blocks += jobs.flat[j] ? (int)((n_elems[j] + 255) / 256) : (int)((n_elems[j] + 31) / 32);
+        } else { jobs.out[j] = nullptr; jobs.parts[j] = nullptr; jobs.n[j] = 0; jobs.n_parts[j] = 0; jobs.flat[j] = 1; }
+    }
+    jobs.first_block[3] = blocks;
+    for (int j = n_jobs; j < 3; ++j) jobs.first_block[j] = blocks;   // empty jobs own no blocks
+    if (blocks) k_reduce<<<blocks, 256, 0, st>>>(jobs);
+}
+
 void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st) {
-    const int blocks = (int)((n_elems + 255) / 256);
-    k_reduce<<<blocks, 256, 0, st>>>(out, partials, n_elems, n_parts);
+    double* o[1] = {out}; const double* p[1] = {partials}; int64_t n[1] = {n_elems}; int np[1] = {n_parts};
+    launch_reduce_jobs(1, o, p, n, np, st);
 }
 
 }  // namespace ib

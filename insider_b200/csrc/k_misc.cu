@@ -43,12 +43,14 @@ __global__ void __launch_bounds__(256) k_count_bits(const uint32_t* __restrict__
 }
 
 __global__ void k_sse_reduce(const double* __restrict__ partial, int n_blocks, CheckState* st) {
-    const int t = threadIdx.x;
-    if (t < 4) {
-        double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * 4 + t];
-        (&st->sse_train)[t] = s;
-    }
+    // 4 quantities x 32 lanes: lane l sums blocks l, l+32, ... then a fixed xor tree over lanes
+    __shared__ double red[4][32];
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < n_blocks; b += 32) s += partial[(size_t)b * 4 + q];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) (&st->sse_train)[q] = s;
+    (void)red;
 }
 
 // src/utils.cpp:56-102 (rmse, loss terms) and src/optimize.cpp:381-408 (delta, decay ladder, convergence)
@@ -118,7 +120,7 @@ void launch_count_bits(const uint32_t* m, int64_t n_words, unsigned long long* o
     k_count_bits<<<blocks, 256, 0, st>>>(m, n_words, out);
 }
 
-void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, cudaStream_t st) { k_sse_reduce<<<1, 32, 0, st>>>(partial, n_blocks, state); }
+void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, cudaStream_t st) { k_sse_reduce<<<1, 128, 0, st>>>(partial, n_blocks, state); }
 
 void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, int iter, void* record_out, cudaStream_t st) {
     k_check<<<1, 256, 0, st>>>(state, A_all, n_A, initial, iter, (insider_check*)record_out);

@@ -3,7 +3,7 @@
 // The reference adds one confounder's contribution back to a dense N x P residual, solves per level, and subtracts
 // it again (src/optimize.cpp:335-362), i.e. 2C-1 read-modify-write passes over N x P per iteration. With
 //     B_k  = sum_j m_kj y_kj v_j          (k_row_b)
-//     Gk_k = sum_j m_kj v_j v_j^T = G - D_k   (k_gram_v, k_row_comp_gram)
+//     Gk_k = sum_j m_kj v_j v_j^T = G - D_k   (accumulated in k_row_b; k_row_comp_gram)
 // the normal equations of level s of confounder c (src/optimize.cpp:150-176 / :178-191) are
 //     XtX_s = sum_{k in s} Gk_k + lambda I ,   Xty_s = sum_{k in s} [ B_k - Gk_k (u_k - a_{c,s}) ]
 // where u_k is the current row factor (Gauss-Seidel: blocks updated earlier in the same iteration are already in u_k).
@@ -21,22 +21,24 @@ namespace {
 
 constexpr int LG_ROWS = 32;      // rows per k_level_gram chunk
 
-// warp Cholesky on an odd-pitch shared matrix (lane = row)
+// warp Cholesky on an odd-pitch shared matrix (lane = row). Each lane only ever writes its own row, the pivot column
+// travels by shuffle, so the trailing update needs no barrier inside the m loop.
 __device__ bool chol_factor(double* S, int ld, int K, int lane) {
     bool ok = true;
     for (int j = 0; j < K; ++j) {
+        __syncwarp();
         const double ajj = S[j * ld + j];
         if (!(ajj > 0.0)) ok = false;
         const double dj = sqrt(ajj);
-        __syncwarp();
         double lij = 0.0;
         if (lane == j) S[j * ld + j] = dj;
         if (lane > j && lane < K) { lij = S[lane * ld + j] / dj; S[lane * ld + j] = lij; }
-        __syncwarp();
-        for (int m = j + 1; m < K; ++m)
-            if (lane >= m && lane < K) S[lane * ld + m] = fma(-lij, S[m * ld + j], S[lane * ld + m]);
-        __syncwarp();
+        for (int m = j + 1; m < K; ++m) {
+            const double lmj = __shfl_sync(FULL, lij, m);
+            if (lane >= m && lane < K) S[lane * ld + m] = fma(-lij, lmj, S[lane * ld + m]);
+        }
     }
+    __syncwarp();
     return ok;
 }
 __device__ double chol_subst(const double* S, int ld, int K, int lane, double b) {
@@ -54,8 +56,8 @@ __device__ double chol_subst(const double* S, int ld, int K, int lane, double b)
     }
     return b;
 }
-// substitution with a stored factor: Lf[KP*KP] row-major lower triangle, Lf[KP*KP + i] = 1 / L_ii
-__device__ double chol_subst_stored(const double* __restrict__ Lf, int KP, int K, int lane, double b) {
+// substitution with a stored factor (staged in shared memory): Lf[KP*KP] row-major lower triangle, Lf[KP*KP + i] = 1 / L_ii
+__device__ double chol_subst_stored(const double* Lf, int KP, int K, int lane, double b) {
     const double* inv = Lf + KP * KP;
     for (int i = 0; i < K; ++i) {
         double xi = b * inv[i];
@@ -146,19 +148,41 @@ __global__ void __launch_bounds__(128) k_level_update(int K, int KP, int masked,
                                                       const int* __restrict__ level_start, double* __restrict__ A, const double* __restrict__ G,
                                                       const double* __restrict__ B, const double* __restrict__ T, const double* __restrict__ Lfac,
                                                       int lfac_base, double* __restrict__ U) {
+    constexpr int RCH = 256;                           // rows staged per pass
+    __shared__ int rows[RCH];
     __shared__ double part[4][2][32];
     __shared__ double delta_s[32];
+    __shared__ double Lf_s[32 * 32 + 32];              // this level's Cholesky factor + inverse diagonal
     const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = level_start[s], e = level_start[s + 1];
     if (e == b) return;
+    {
+        const double* src = Lfac + (size_t)(lfac_base + s) * (KP * KP + KP);
+        for (int x = threadIdx.x; x < KP * KP + KP; x += 128) Lf_s[x] = src[x];
+    }
     double p0 = 0.0, p1 = 0.0;     // masked: p0 = sum T ; dense: p0 = sum B, p1 = sum u
-    if (lane < KP) {
-        const double* src0 = masked ? T : B;
-#pragma unroll 4
-        for (int r = b + warp; r < e; r += 4) {
-            const int k = rows_sorted[r];
-            p0 += src0[(size_t)k * KP + lane];
-            if (!masked) p1 += U[(size_t)k * KP + lane];
+    const double* src0 = masked ? T : B;
+    for (int c0 = b; c0 < e; c0 += RCH) {
+        const int n = min(RCH, e - c0);
+        __syncthreads();
+        for (int x = threadIdx.x; x < n; x += 128) rows[x] = rows_sorted[c0 + x];
+        __syncthreads();
+        if (lane < KP) {
+            int r = warp;
+            for (; r + 12 < n; r += 16) {              // four rows in flight per warp
+                const int k0 = rows[r], k1 = rows[r + 4], k2 = rows[r + 8], k3 = rows[r + 12];
+                const double a0 = src0[(size_t)k0 * KP + lane], a1 = src0[(size_t)k1 * KP + lane], a2 = src0[(size_t)k2 * KP + lane], a3 = src0[(size_t)k3 * KP + lane];
+                p0 += a0; p0 += a1; p0 += a2; p0 += a3;
+                if (!masked) {
+                    const double u0 = U[(size_t)k0 * KP + lane], u1 = U[(size_t)k1 * KP + lane], u2 = U[(size_t)k2 * KP + lane], u3 = U[(size_t)k3 * KP + lane];
+                    p1 += u0; p1 += u1; p1 += u2; p1 += u3;
+                }
+            }
+            for (; r < n; r += 4) {
+                const int k = rows[r];
+                p0 += src0[(size_t)k * KP + lane];
+                if (!masked) p1 += U[(size_t)k * KP + lane];
+            }
         }
     }
     part[warp][0][lane] = p0; part[warp][1][lane] = p1;
@@ -176,15 +200,30 @@ __global__ void __launch_bounds__(128) k_level_update(int K, int KP, int masked,
             }
             rhs -= acc;
         }
-        const double x = chol_subst_stored(Lfac + (size_t)(lfac_base + s) * (KP * KP + KP), KP, K, lane, rhs);   // :175 / :190
+        const double x = chol_subst_stored(Lf_s, KP, K, lane, rhs);   // :175 / :190
         double dlt = 0.0;
         if (lane < K) { dlt = x - a_old; A[(size_t)s * KP + lane] = x; }
         delta_s[lane] = dlt;
     }
     __syncthreads();
-    if (lane < KP) {
-        const double dlt = delta_s[lane];
-        for (int r = b + warp; r < e; r += 4) U[(size_t)rows_sorted[r] * KP + lane] += dlt;
+    const double dlt = delta_s[lane];
+    for (int c0 = b; c0 < e; c0 += RCH) {
+        const int n = min(RCH, e - c0);
+        if (e - b > RCH) {                             // indices of this pass (single pass: still staged from above)
+            __syncthreads();
+            for (int x = threadIdx.x; x < n; x += 128) rows[x] = rows_sorted[c0 + x];
+            __syncthreads();
+        }
+        if (lane < KP) {
+            int r = warp;
+            for (; r + 12 < n; r += 16) {
+                double* q0 = U + (size_t)rows[r] * KP + lane; double* q1 = U + (size_t)rows[r + 4] * KP + lane;
+                double* q2 = U + (size_t)rows[r + 8] * KP + lane; double* q3 = U + (size_t)rows[r + 12] * KP + lane;
+                const double u0 = *q0, u1 = *q1, u2 = *q2, u3 = *q3;
+                *q0 = u0 + dlt; *q1 = u1 + dlt; *q2 = u2 + dlt; *q3 = u3 + dlt;
+            }
+            for (; r < n; r += 4) U[(size_t)rows[r] * KP + lane] += dlt;
+        }
     }
 }
 

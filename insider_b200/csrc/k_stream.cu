@@ -28,6 +28,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 struct StreamArgs {
     const double* Y; const uint32_t* trC; const uint32_t* teC; const double* V; const double* Ut;
     double* out;                 // Bp / Xty / partial
+    double* out2;                // k_row_b: Gp[(split*4 + warp)][KP*KP] partial V V^T (slab 0 blocks, warps 0..3)
     int N, K, KP, ldY, ldV, ldT, Wp;
     int n_tiles;                 // gene tiles in total
     int R, n_slabs, pitchS, pitchU;
@@ -106,6 +107,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
     for (int i = 0; i < MT_PER_WARP; ++i)
 #pragma unroll
         for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
+    // gram = V V^T (src/optimize.cpp:332) rides along: the V fragments of k-step ks are already in registers, warp ks
+    // (of warps 0..3, slab 0 only) also accumulates the upper-triangle tiles of sum_j v_j v_j^T
+    const bool do_gram = (slab == 0) && (warp < TG / 4) && (a.out2 != nullptr);
+    double gacc[NT][NT][2];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) gacc[i][n][0] = gacc[i][n][1] = 0.0;
 
     for (int item = 0; item < n_items; ++item) {
         const int s = item % S;
@@ -127,6 +136,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
             double b[NT];
 #pragma unroll
             for (int n = 0; n < NT; ++n) b[n] = Vs[(4 * ks + t) * a.ldV + 8 * n + g];
+            if (do_gram && ks == warp) {
+#pragma unroll
+                for (int n1 = 0; n1 < NT; ++n1)
+#pragma unroll
+                    for (int n2 = n1; n2 < NT; ++n2) dmma(gacc[n1][n2][0], gacc[n1][n2][1], b[n1], b[n2]);
+            }
             const double* yrow = Ys + (4 * ks + t) * a.pitchS + g;
 #pragma unroll
             for (int i = 0; i < MT_PER_WARP; ++i) {
@@ -139,6 +154,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
             }
         }
         __syncthreads();   // stage s may be refilled
+    }
+    if (do_gram) {
+        double* Gp = a.out2 + ((size_t)blockIdx.x * (TG / 4) + warp) * a.KP * a.KP;
+#pragma unroll
+        for (int n1 = 0; n1 < NT; ++n1)
+#pragma unroll
+            for (int n2 = n1; n2 < NT; ++n2)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ra = 8 * n1 + g, cb = 8 * n2 + 2 * t + e;
+                    Gp[ra * a.KP + cb] = gacc[n1][n2][e];
+                    Gp[cb * a.KP + ra] = gacc[n1][n2][e];
+                }
     }
     // store the block's partial: Bp[split][N][KP]
     double* Bp = a.out + (size_t)blockIdx.x * a.N * a.KP;
@@ -440,10 +468,10 @@ int row_b_default_splits(const Geom& g, int sm_count) {
 size_t row_b_partial_elems(const Geom& g, int n_splits) { return (size_t)n_splits * g.N * g.KP; }
 int stream_default_blocks(const Geom& g, int sm_count) { return sm_count < g.n_tiles ? sm_count : g.n_tiles; }
 
-void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, int n_splits,
+void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
                   cudaStream_t st) {
     StreamArgs a = base_args(g);
-    a.Y = Y; a.trC = trC; a.V = V; a.out = Bp; a.n_splits = n_splits;
+    a.Y = Y; a.trC = trC; a.V = V; a.out = Bp; a.out2 = Gp; a.n_splits = n_splits;
     if (g.N <= SINGLE_SLAB_MAX_N) { a.R = g.ldY; a.n_slabs = 1; a.pitchS = g.ldY; }
     else { a.R = SLAB_ROWS_BIG; a.n_slabs = (g.ldY + a.R - 1) / a.R; a.pitchS = pitch4(a.R); }
     const size_t stage = ((size_t)TG * a.pitchS + 8 + (size_t)TG * g.ldV) * 8;

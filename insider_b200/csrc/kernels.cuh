@@ -23,9 +23,10 @@ struct Geom {
 };
 
 // ---- streaming passes over Y (k_stream.cu) ------------------------------------------------------------------
-// B_partial[split][N][K] = sum over the split's genes of (M o Y) V^T
-void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, int n_splits,
+// Bp[split][N][KP] = sum over the split's genes of (M o Y) V^T ; Gp[split*4 + w][KP*KP] = partial V V^T (w = 0..3), fused
+void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
                   cudaStream_t st);
+constexpr int ROW_B_GRAM_PARTS = 4;
 size_t row_b_partial_elems(const Geom& g, int n_splits);
 int row_b_default_splits(const Geom& g, int sm_count);
 // Xty[j][k] = sum_i U[i][k] m_ij y_ij
@@ -37,13 +38,13 @@ void launch_sse(const Geom& g, bool masked, const double* Y, const uint32_t* trC
 int stream_default_blocks(const Geom& g, int sm_count);
 
 // ---- Gram matrices (k_gram.cu) ------------------------------------------------------------------------------
-// Gp[block][KP*KP] partial of V V^T over the block's genes
-void launch_gram_v(const Geom& g, const double* V, double* Gp, int n_blocks, cudaStream_t st);
 // Dp[split][N][KP*KP]: per-row complement Gram sum_{j: m_ij = 0} v_j v_j^T over the split's genes
 void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, double* Dp, int n_splits, cudaStream_t st);
 // fixed-order reductions of the partial buffers:
 //   B[N][K] = sum_s Bp[s] ; G[KP*KP] = sum_b Gp[b] ; D[N][KP*KP] = sum_s Dp[s]
 void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st);
+// the same for up to three buffers in one launch
+void launch_reduce_jobs(int n_jobs, double* const* out, const double* const* parts, const int64_t* n_elems, const int* n_parts, cudaStream_t st);
 
 // ---- row side (k_rows.cu) -----------------------------------------------------------------------------------
 struct RowDesign {            // one categorical confounder
@@ -90,7 +91,7 @@ struct CdParams {
 void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, double* XtXall, cudaStream_t st);
 // per gene: alpha == 0 -> ridge solve, else elastic-net CD (persistent groups pulling genes from `queue`). Updates V in place.
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
-                      unsigned long long* sweeps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st);
+                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st);
 // stand-alone batched solver (insider_b200_strong_cd): XtX column-major K x K, either shared or per column [n][K*K]
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,

@@ -125,7 +125,7 @@ struct insider_session {
     int total_levels = 0, max_chunks = 1;
     LevelTable* tab_dev = nullptr;
     double* Lfac = nullptr;             // [total_levels][KP*KP + KP] Cholesky factors + inverse diagonals
-    int rb_splits = 1, gv_blocks = 1, d_splits = 1, stream_blocks = 1;
+    int rb_splits = 1, d_splits = 1, stream_blocks = 1;
     RowDesign* designs_dev = nullptr;
     std::vector<RowDesign> designs;
     CheckState* state = nullptr;
@@ -371,13 +371,15 @@ void run_iteration(insider_session* s) {
     const Geom& g = s->g;
     const int KK = g.KP * g.KP;
     // sufficient statistics of the row update: G = V V' (:332), B = (M o Y) V', D_k = complement Grams
-    { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->Gp, s->gv_blocks, st); }
-    { Launch l(s, "k_reduce"); launch_reduce_partials(s->G, s->Gp, KK, s->gv_blocks, st); }
-    { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->rb_splits, st); }
-    { Launch l(s, "k_reduce"); launch_reduce_partials(s->B, s->Bp, (int64_t)g.N * g.KP, s->rb_splits, st); }
-    if (s->masked) {
-        { Launch l(s, "k_row_comp_gram"); launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st); }
-        { Launch l(s, "k_reduce"); launch_reduce_partials(s->D, s->Dp, (int64_t)g.N * KK, s->d_splits, st); }
+    { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st); }
+    if (s->masked) { Launch l(s, "k_row_comp_gram"); launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st); }
+    {
+        double* outs[3] = {s->B, s->G, s->D};
+        const double* parts[3] = {s->Bp, s->Gp, s->Dp};
+        const int64_t ns[3] = {(int64_t)g.N * g.KP, KK, (int64_t)g.N * KK};
+        const int nps[3] = {s->rb_splits, s->rb_splits * ROW_B_GRAM_PARTS, s->d_splits};
+        Launch l(s, "k_reduce");
+        launch_reduce_jobs(s->masked ? 3 : 2, outs, parts, ns, nps, st);
     }
     if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->stats, s->stats, s->stats_elems, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(stats)");
     // normal-equation matrices of every level of every confounder: assembled and factorised once (they do not depend on A)
@@ -403,7 +405,7 @@ void run_iteration(insider_session* s) {
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
-    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->queue, s->err_dev, s->ctx->sm_count, st); }
+    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->err_dev, s->ctx->sm_count, st); }
 }
 
 insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* f, const insider_options* o) {
@@ -447,8 +449,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->B = s->stats; s->G = s->B + (size_t)g.N * g.KP; s->D = s->masked ? s->G + KK : nullptr;
         s->rb_splits = row_b_default_splits(g, ctx->sm_count);
         s->Bp = s->pool.get<double>(row_b_partial_elems(g, s->rb_splits), true, st);
-        s->gv_blocks = std::max(1, std::min(ctx->sm_count, (int)(g.P_pad / 64)));
-        s->Gp = s->pool.get<double>((size_t)s->gv_blocks * KK, true, st);
+        s->Gp = s->pool.get<double>((size_t)s->rb_splits * ROW_B_GRAM_PARTS * KK, true, st);
         s->stream_blocks = stream_default_blocks(g, ctx->sm_count);
         s->sse_part = s->pool.get<double>((size_t)s->stream_blocks * 4, true, st);
         s->T = s->pool.get<double>((size_t)g.N * g.KP, true, st);
@@ -491,7 +492,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         CUDA_TRY(cudaMemcpyAsync(s->state, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
         s->max_records = (uint32_t)std::min<uint64_t>((uint64_t)o->max_iter / s->opt.check_every + 3, 1u << 20);
         s->records_dev = s->pool.get<insider_check>(s->max_records, true, st);
-        s->sweeps_dev = s->pool.get<unsigned long long>(1, true, st);
+        s->sweeps_dev = s->pool.get<unsigned long long>(2, true, st);   // [sweeps, coordinate steps]
         s->queue = s->pool.get<unsigned int>(1, true, st);
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
@@ -563,14 +564,15 @@ void do_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms) {
 
 void fill_result(insider_session* s, insider_result* res) {
     if (!res) return;
-    unsigned long long sw = 0; int err = 0;
-    CUDA_TRY(cudaMemcpy(&sw, s->sweeps_dev, 8, cudaMemcpyDeviceToHost));
+    unsigned long long sw2[2] = {0, 0}; int err = 0;
+    CUDA_TRY(cudaMemcpy(sw2, s->sweeps_dev, 16, cudaMemcpyDeviceToHost));
+    const unsigned long long sw = sw2[0];
     CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));
     res->train_rmse = s->last.train_rmse; res->test_rmse = s->last.test_rmse; res->loss = s->last.loss;
     res->iters_run = s->iter;
     res->n_checks = (uint32_t)std::min<size_t>(s->records.size(), res->checks ? res->max_checks : s->records.size());
     if (res->checks) for (uint32_t i = 0; i < res->n_checks; ++i) res->checks[i] = s->records[i];
-    res->cd_sweeps = (int64_t)sw; res->loop_ms = s->loop_ms; res->h2d_bytes = s->h2d; res->d2h_bytes = s->d2h; res->kernel_launches = s->launches;
+    res->cd_sweeps = (int64_t)sw; res->cd_steps = (int64_t)sw2[1]; res->loop_ms = s->loop_ms; res->h2d_bytes = s->h2d; res->d2h_bytes = s->d2h; res->kernel_launches = s->launches;
     if (err) throw Err{INSIDER_ERR_NOT_SPD, "a normal-equation matrix was not positive definite"};
 }
 
@@ -788,9 +790,8 @@ int insider_b200_fit_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t
         try {
             cudaStream_t st = ctx->stream;
             const Geom& g = s->g; const int KK = g.KP * g.KP;
-            launch_gram_v(g, s->V, s->Gp, s->gv_blocks, st);
-            launch_reduce_partials(s->G, s->Gp, KK, s->gv_blocks, st);
-            launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->rb_splits, st);
+            launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st);
+            launch_reduce_partials(s->G, s->Gp, KK, s->rb_splits * ROW_B_GRAM_PARTS, st);
             launch_reduce_partials(s->B, s->Bp, (int64_t)g.N * g.KP, s->rb_splits, st);
             if (s->masked) {
                 launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st);

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libinsider_b200.so")
+LIB_PATH = os.environ.get("INSIDER_B200_LIB") or os.path.join(_HERE, "lib", "libinsider_b200.so")   # env override: A/B builds
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NCCL, ERR_NOT_SPD, ERR_DIVERGED, ERR_EMPTY_TEST_SET, ERR_NOMEM, ERR_UNSUPPORTED = range(9)
 MASK_NONE, MASK_INT32, MASK_UINT8, MASK_DOUBLE = range(4)

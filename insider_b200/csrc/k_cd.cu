@@ -155,6 +155,7 @@ struct CdArgs {
     uint64_t seed; int perm_mode;
     unsigned long long* sweeps_total; unsigned long long* steps_total; int* sweeps_per_gene;
     unsigned int* queue;          // atomic gene counter (zeroed before launch)
+    const unsigned char* perm_table;   // [32][PERM_T][32] rank tables (common.cuh)
 };
 
 // persistent elastic-net solver: every 8-lane group repeatedly claims a gene, solves it, writes it back
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     bool active = false, retired = false;
     uint32_t inc = 0, draw = 0;
     int n_inc = 0, sweeps = 0;
+    uint32_t row_w = 0, row_draw = 0; int row_n = -1;          // prefetched permutation-table word (see below)
     unsigned long long sweeps_acc = 0, steps_acc = 0;
 
     while (true) {
@@ -256,38 +258,32 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     Bc[c] = beta[s]; Qc[c] = q[s]; Dc[c] = d; DENc[c] = den; RDc[c] = 1.0 / den;
                 }
                 __syncwarp(gmask);
-                n_inc = __popc(inc); draw = 0; sweeps = 0; active = true;
+                n_inc = __popc(inc); draw = 0; sweeps = 0; active = true; row_n = -1;
             }
         }
         if (__all_sync(FULL, retired)) break;
 
-        // ---- visiting order (coordinate_descent.cpp:89): rank of every coordinate, computed in coordinate layout
+        // ---- visiting order (coordinate_descent.cpp:89): position of every coordinate in this sweep. Active coordinates take
+        //      the permutation selected from the table by the per-sweep key; inactive ones keep ascending order behind them.
         int pos[SL];
         {
-            uint32_t key[SL];
-            const uint64_t pk = key_iter ^ mix64((uint64_t)(a.gene0 + gene) * 0xD1B54A32D192ED03ull + (uint64_t)draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+            // lane li holds 4-byte word li of the 32-byte rank row; the row of the NEXT sweep is prefetched one sweep ahead
+            auto row_word = [&](uint32_t dr) -> const uint32_t* {
+                const uint64_t pk = key_iter ^ mix64((uint64_t)(a.gene0 + gene) * 0xD1B54A32D192ED03ull + (uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+                return reinterpret_cast<const uint32_t*>(a.perm_table + ((size_t)(max(n_inc, 1) - 1) * PERM_T + perm_select(pk)) * 32) + li;
+            };
+            if (row_n != n_inc || row_draw != draw) row_w = __ldg(row_word(draw));       // new gene or changed active set
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 const int c = s * LPG + li;
                 const uint32_t below = (1u << c) - 1u;
+                const int p_act = __popc(inc & below) & 31;
                 const bool on = (inc >> c) & 1u;
-                const uint32_t kv = (a.perm_mode == 1) ? ((perm_value(pk, __popc(inc & below)) << 5) | (uint32_t)c) : (uint32_t)c;
-                key[s] = on ? kv : 0xffffffffu;                                   // inactive keys never rank below an active one
-                pos[s] = (c < K) ? n_inc + __popc(~inc & valid_mask & below) : c; // inactive keep ascending order behind the active ones
+                const uint32_t w = __shfl_sync(FULL, row_w, p_act >> 2, LPG);
+                const int p_perm = (a.perm_mode == 1) ? (int)((w >> (8 * (p_act & 3))) & 0xffu) : p_act;
+                pos[s] = on ? p_perm : ((c < K) ? n_inc + __popc(~inc & valid_mask & below) : c);
             }
-            int rank[SL];
-#pragma unroll
-            for (int s = 0; s < SL; ++s) rank[s] = 0;
-#pragma unroll
-            for (int ms = 0; ms < SL; ++ms)
-#pragma unroll
-                for (int ml = 0; ml < LPG; ++ml) {
-                    const uint32_t km = __shfl_sync(FULL, key[ms], ml, LPG);
-#pragma unroll
-                    for (int s = 0; s < SL; ++s) rank[s] += (km < key[s]) ? 1 : 0;
-                }
-#pragma unroll
-            for (int s = 0; s < SL; ++s) if ((inc >> (s * LPG + li)) & 1u) pos[s] = rank[s];
+            row_w = __ldg(row_word(draw + 1)); row_n = n_inc; row_draw = draw + 1;       // consumed by the next sweep
         }
         ++draw;
         __syncwarp();
@@ -310,27 +306,42 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
             cdo[s] = xbase + (uint32_t)c * 8u;
             rowoff[s] = c * XLD * 8;
         }
-        // ---- one sweep; step i is owned by lane (i & 7), slot (i >> 3)
+        // ---- one sweep; step i is owned by lane (i & 7), slot (i >> 3). The XtX row of step i+1 does not depend on the
+        //      update chain, so it is fetched one step ahead (its shared-memory latency hides behind the chain of step i).
+        double xv[SL];
+        {
+            const uint32_t ro0 = (uint32_t)__shfl_sync(FULL, rowoff[0], 0, LPG);
+#pragma unroll
+            for (int s = 0; s < SL; ++s) xv[s] = lds64(ro0 + cdo[s]);
+        }
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
             if (i >= nmax) break;
             const int si = i >> 3, ow = i & 7;
+            double xn[SL];
+            if (i + 1 < KP) {
+                const uint32_t ron = (uint32_t)__shfl_sync(FULL, rowoff[(i + 1) >> 3], (i + 1) & 7, LPG);
+#pragma unroll
+                for (int s = 0; s < SL; ++s) xn[s] = lds64(ron + cdo[s]);
+            }
             const double bo = b[si];
             const double up = fma(bo, d[si], q[si]);                             // :94
             const double t1 = fabs(up) - lap[si];
-            double nb = 0.0;
-            if (t1 > 0.0) {                                                      // :99-104
-                const double num = copysign(t1, up);
-                nb = num * rd[si];                                               // correctly rounded num / den (Markstein)
-                nb = fma(fma(-den[si], nb, num), rd[si], nb);
-            }
-            // positions beyond n_on hold excluded coordinates (beta = 0) and have lap = INF: nb = 0, dlt = 0
+            // :99-104, branch-free: correctly rounded copysign(t1, up) / den (reciprocal + Markstein), 0 when t1 <= 0.
+            // Positions beyond n_on hold excluded coordinates (beta = 0) and have lap = INF: t1 = -INF -> nb = 0 -> dlt = 0.
+            const double num = copysign(t1, up);
+            double nb = num * rd[si];
+            nb = fma(fma(-den[si], nb, num), rd[si], nb);
+            nb = (t1 > 0.0) ? nb : 0.0;
             const double dlt = nb - bo;
             const double dkk = __shfl_sync(FULL, dlt, ow, LPG);
-            const uint32_t ro = (uint32_t)__shfl_sync(FULL, rowoff[si], ow, LPG);
             if (li == ow) { b[si] = nb; upsave[si] = up; }                        // :106-109 (loss decrement: after the sweep)
 #pragma unroll
-            for (int s = 0; s < SL; ++s) q[s] = fma(-dkk, lds64(ro + cdo[s]), q[s]);
+            for (int s = 0; s < SL; ++s) q[s] = fma(-dkk, xv[s], q[s]);
+            if (i + 1 < KP) {
+#pragma unroll
+                for (int s = 0; s < SL; ++s) xv[s] = xn[s];
+            }
         }
         // ---- loss change of the sweep, dL = sum_k (new-old)((XtX_kk + l2)(new+old)/2 - upper_k) + lambda alpha(|new|-|old|),
         //      evaluated for all slots at once (Bc still holds the pre-sweep values); then scatter back to coordinate layout
@@ -461,7 +472,8 @@ void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const 
 }
 
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
-                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st) {
+                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
+                      int sm_count, cudaStream_t st) {
     if (g.P == 0) return;
     if (p.alpha == 0.0) {
         RidgeArgs r{UtU, XtXall, Xty, V, g.K, g.KP, g.ldV, g.P, p.lambda, err_flag};
@@ -475,14 +487,15 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
     a.Xsh = UtU; a.Xall = XtXall; a.x_stride = (int64_t)g.KP * g.KP; a.xs_r = g.KP; a.xs_c = 1;
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P; a.gene0 = g.gene0;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
-    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = nullptr; a.queue = queue;
+    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = nullptr; a.queue = queue; a.perm_table = perm_table;
     launch_cd(a, g.KP, masked, sm_count, st);
 }
 
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,
-                     unsigned int* queue, int sm_count, cudaStream_t st) {
+                     unsigned int* queue, const unsigned char* perm_table, int sm_count, cudaStream_t st) {
     CdArgs a{};
+    a.perm_table = perm_table;
     a.Xsh = XtX; a.Xall = XtX; a.x_stride = (int64_t)K * K; a.xs_r = 1; a.xs_c = K;      // caller's column-major K x K
     a.Xty = Xty; a.W0 = w0; a.Vout = beta; a.ldv = K; a.K = K; a.P = n; a.gene0 = (int64_t)gene0;
     a.lambda = lambda; a.alpha = alpha; a.tol_dev = nullptr; a.tol_host = tol; a.als_iter_dev = nullptr; a.als_iter_host = als_iter;

@@ -91,11 +91,12 @@ struct CdParams {
 void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, double* XtXall, cudaStream_t st);
 // per gene: alpha == 0 -> ridge solve, else elastic-net CD (persistent groups pulling genes from `queue`). Updates V in place.
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
-                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, int* err_flag, int sm_count, cudaStream_t st);
+                      unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
+                      int sm_count, cudaStream_t st);
 // stand-alone batched solver (insider_b200_strong_cd): XtX column-major K x K, either shared or per column [n][K*K]
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,
-                     unsigned int* queue, int sm_count, cudaStream_t st);
+                     unsigned int* queue, const unsigned char* perm_table, int sm_count, cudaStream_t st);
 
 // ---- misc (k_misc.cu) ---------------------------------------------------------------------------------------
 // src: n_genes columns of N mask elements (INSIDER_MASK_* kind) -> dstC[n_genes][Wp] bit-packed

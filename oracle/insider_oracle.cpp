@@ -23,8 +23,9 @@
 //
 // Permutation modes for the coordinate order (coordinate_descent.cpp:89):
 //   mode 0 (A) R-stream-faithful: one global R RNG consumed gene after gene (single-thread semantics).
-//   mode 1 (B) counter-based: keys (seed, als_iter, gene, draw) -> 26-bit values, sorted ascending with
-//              index tie-break. Identical on CPU and GPU; parity at scale is defined in this mode.
+//   mode 1 (B) counter-based: key (seed, als_iter, gene, draw) selects one of 4096 table permutations of the active-set
+//              size, each built like randperm (sort 26-bit random keys, index tie-break). Identical on CPU and GPU;
+//              parity at scale is defined in this mode.
 //   mode 2     identity order (no shuffling) - for analytic tests.
 
 #include <algorithm>
@@ -113,8 +114,12 @@ void randperm(PermSrc& ps, int n, int* ord) {
             pk[i] = {(uint32_t)(int)u, i};
         }
     } else if (ps.mode == 1) {
-        uint64_t key = mix64(ps.seed + 0x9E3779B97F4A7C15ull * (1ull + ps.als_iter)) ^
-                       mix64(ps.gene * 0xD1B54A32D192ED03ull + (uint64_t)ps.draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+        // mode B: the per-sweep key selects one of PERM_T table permutations of size n; every table entry is built like
+        // randperm itself (sort n 26-bit random keys ascending, ties by index) from a fixed table key.
+        const uint64_t sel = mix64(ps.seed + 0x9E3779B97F4A7C15ull * (1ull + ps.als_iter)) ^
+                            mix64(ps.gene * 0xD1B54A32D192ED03ull + (uint64_t)ps.draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+        const uint64_t t = (sel >> 20) & 4095ull;
+        const uint64_t key = mix64(0x1F83D9ABFB41BD6Bull ^ (((uint64_t)n << 32) | t));
         for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)) >> 38), i};
     } else {
         for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)i, i};

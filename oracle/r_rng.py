@@ -180,7 +180,9 @@ def randperm_b(seed: int, als_iter: int, gene: int, draw: int, n: int) -> np.nda
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m64
         return z ^ (z >> 31)
 
-    key = mix64(seed + 0x9E3779B97F4A7C15 * (1 + als_iter)) ^ mix64(
+    pk = mix64(seed + 0x9E3779B97F4A7C15 * (1 + als_iter)) ^ mix64(
         gene * 0xD1B54A32D192ED03 + draw * 0x8CB92BA72F3D8DD7 + 0x2545F4914F6CDD1D)
+    t = (pk >> 20) & 4095                                     # table entry (4096 permutations per size)
+    key = mix64(0x1F83D9ABFB41BD6B ^ ((n << 32) | t))
     vals = np.array([mix64(key + 0x9E3779B97F4A7C15 * (i + 1)) >> 38 for i in range(n)], dtype=np.int64)
     return np.argsort(vals, kind="stable")

@@ -12,8 +12,12 @@
 // XtX_s does not depend on the factors, so all levels of all confounders are assembled and Cholesky-factorised up front
 // by one launch (k_level_factor: one warp per level, batched K x K factorisations in shared memory); the per-confounder
 // launches then only form right-hand sides, substitute, and shift the rows of U.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ib {
 
@@ -227,6 +231,116 @@ __global__ void __launch_bounds__(128) k_level_update(int K, int KP, int masked,
     }
 }
 
+// ---- dense path (tuning = 0): the whole Gauss-Seidel sweep over confounders without touching N-length data ----------
+// sum_{k in s} u_k = sum_{c' != c} sum_{s'} n(c,s;c',s') a_{c',s'} + n_s a_{c,s} + (sum_{k in s} x_k) W, where n(.) are the
+// co-occurrence counts of the design (fixed). The right-hand side of level s of confounder c is therefore
+//     SB_{c,s} - G ( sum_{c' != c} sum_{s'} n a_{c',s'} + Sx_{c,s} W ),        SB_{c,s} = sum_{k in s} B_k
+// k_level_sumB forms SB for every level of every confounder in one launch; k_rows_dense_gs then runs the C block updates
+// back to back in ONE block (one warp per level, __syncthreads between confounders), reading only factor-sized data.
+__global__ void __launch_bounds__(128) k_level_sumB(const LevelTable* __restrict__ tab, int KP, const double* __restrict__ B, double* __restrict__ SB) {
+    constexpr int RCH = 256;
+    __shared__ int rows[RCH];
+    __shared__ double part[4][32];
+    const LevelTable t = tab[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double p0 = 0.0;
+    for (int c0 = t.row_begin; c0 < t.row_end; c0 += RCH) {
+        const int n = min(RCH, t.row_end - c0);
+        __syncthreads();
+        for (int x = threadIdx.x; x < n; x += 128) rows[x] = t.rows_sorted[c0 + x];
+        __syncthreads();
+        if (lane < KP) {
+            int r = warp;
+            for (; r + 12 < n; r += 16) {
+                const double a0 = B[(size_t)rows[r] * KP + lane], a1 = B[(size_t)rows[r + 4] * KP + lane];
+                const double a2 = B[(size_t)rows[r + 8] * KP + lane], a3 = B[(size_t)rows[r + 12] * KP + lane];
+                p0 += a0; p0 += a1; p0 += a2; p0 += a3;
+            }
+            for (; r < n; r += 4) p0 += B[(size_t)rows[r] * KP + lane];
+        }
+    }
+    part[warp][lane] = p0;
+    __syncthreads();
+    if (warp == 0 && lane < KP) SB[(size_t)blockIdx.x * KP + lane] = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+}
+
+struct DenseGsArgs {
+    int C, K, KP, Q;
+    const int* lvl_first;        // [C+1] first global level index of each confounder
+    const int* co_ptr;           // [total_levels+1] CSR over levels: co-occurring (other-confounder) levels
+    const int* co_row;           // [nnz] row of A_all (global level index) of the co-occurring level
+    const double* co_cnt;        // [nnz] number of samples in both levels
+    const double* Sx;            // [total_levels][Q] sum of each continuous covariate over the level's samples (or null)
+    const double* W;             // [Q][KP] continuous factor (or null)
+    double* A_all;               // [total_levels][KP]
+    const double* SB;            // [total_levels][KP]
+    const double* G;             // [KP*KP]
+    const double* Lfac;          // [total_levels][KP*KP + KP]
+    int a_in_smem;               // 1: the categorical factors fit in shared memory next to the per-warp factor buffers
+};
+constexpr int GS_CLUSTER = 8;       // CTAs per cluster (portable maximum)
+constexpr int GS_WARPS = 16;        // warps per CTA -> 128 levels in flight
+__global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 32, 1) k_rows_dense_gs(DenseGsArgs a) {
+    extern __shared__ double gs_smem[];                // G [KP*KP] | A copy [total_levels*KP] (if a.a_in_smem) | per-warp factor [KP*KP + KP]
+    cg::cluster_group cluster = cg::this_cluster();
+    const int KP = a.KP, K = a.K, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = (int)cluster.block_rank() * GS_WARPS + warp, n_gw = GS_CLUSTER * GS_WARPS;
+    const int FK = KP * KP + KP;
+    const int n_lv = a.lvl_first[a.C];
+    double* Gs = gs_smem;
+    double* As = gs_smem + KP * KP;                                            // this CTA's copy of all categorical factors
+    double* Lw = As + (a.a_in_smem ? (size_t)n_lv * KP : 0) + (size_t)warp * FK;
+    for (int x = threadIdx.x; x < KP * KP; x += blockDim.x) Gs[x] = a.G[x];
+    const double* Asrc = a.a_in_smem ? As : a.A_all;
+    for (int c = 0; c < a.C; ++c) {                                            // src/optimize.cpp:335 (fixed block order)
+        // (re)load the factors: blocks updated earlier in this sweep were written by other CTAs of the cluster
+        if (a.a_in_smem) for (int x = threadIdx.x; x < n_lv * KP; x += blockDim.x) As[x] = __ldcg(a.A_all + x);
+        __syncthreads();
+        for (int lv = a.lvl_first[c] + gw; lv < a.lvl_first[c + 1]; lv += n_gw) {
+            // stage this level's Cholesky factor (independent loads, issued before anything depends on them)
+            const double* Lf = a.Lfac + (size_t)lv * FK;
+            for (int x = lane; x < FK; x += 32) Lw[x] = Lf[x];
+            // w = sum over co-occurring levels of count * a_{c',s'}: 32 CSR entries per batch, broadcast by shuffle
+            double w = 0.0;
+            const int e0 = a.co_ptr[lv], e1 = a.co_ptr[lv + 1];
+            for (int eb = e0; eb < e1; eb += 32) {
+                const int n = min(32, e1 - eb);
+                const int myrow = (lane < n) ? a.co_row[eb + lane] : 0;
+                const double mycnt = (lane < n) ? a.co_cnt[eb + lane] : 0.0;
+                int j = 0;
+                for (; j + 3 < n; j += 4) {
+                    const int r0 = __shfl_sync(FULL, myrow, j), r1 = __shfl_sync(FULL, myrow, j + 1), r2 = __shfl_sync(FULL, myrow, j + 2), r3 = __shfl_sync(FULL, myrow, j + 3);
+                    const double c0 = __shfl_sync(FULL, mycnt, j), c1 = __shfl_sync(FULL, mycnt, j + 1), c2 = __shfl_sync(FULL, mycnt, j + 2), c3 = __shfl_sync(FULL, mycnt, j + 3);
+                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    if (lane < KP) {
+                        if (a.a_in_smem) { v0 = As[(size_t)r0 * KP + lane]; v1 = As[(size_t)r1 * KP + lane]; v2 = As[(size_t)r2 * KP + lane]; v3 = As[(size_t)r3 * KP + lane]; }
+                        else { v0 = __ldcg(Asrc + (size_t)r0 * KP + lane); v1 = __ldcg(Asrc + (size_t)r1 * KP + lane); v2 = __ldcg(Asrc + (size_t)r2 * KP + lane); v3 = __ldcg(Asrc + (size_t)r3 * KP + lane); }
+                    }
+                    w = fma(c0, v0, w); w = fma(c1, v1, w); w = fma(c2, v2, w); w = fma(c3, v3, w);
+                }
+                for (; j < n; ++j) {
+                    const int r0 = __shfl_sync(FULL, myrow, j);
+                    const double c0 = __shfl_sync(FULL, mycnt, j);
+                    if (lane < KP) w = fma(c0, a.a_in_smem ? As[(size_t)r0 * KP + lane] : __ldcg(Asrc + (size_t)r0 * KP + lane), w);
+                }
+            }
+            if (lane < KP) for (int q = 0; q < a.Q; ++q) w = fma(a.Sx[(size_t)lv * a.Q + q], a.W[(size_t)q * KP + lane], w);
+            double acc = 0.0;
+            for (int m = 0; m < KP; ++m) {
+                const double wm = __shfl_sync(FULL, w, m);
+                if (lane < KP) acc = fma(Gs[m * KP + lane], wm, acc);
+            }
+            const double rhs = (lane < KP) ? a.SB[(size_t)lv * KP + lane] - acc : 0.0;
+            __syncwarp();
+            const double x = chol_subst_stored(Lw, KP, K, lane, rhs);         // :190
+            if (lane < K) a.A_all[(size_t)lv * KP + lane] = x;
+            __syncwarp();
+        }
+        __threadfence();
+        cluster.sync();                                                        // block c is complete and visible cluster-wide
+    }
+}
+
 // continuous covariate, stage 1: per chunk of 64 rows  H_c = sum x_k^2 M_k ,  T_c = sum x_k (B_k - M_k u_k)
 __global__ void __launch_bounds__(256) k_cont_partial(int N, int KP, const double* __restrict__ x, const double* __restrict__ B,
                                                       const double* __restrict__ G, const double* __restrict__ D, const double* __restrict__ U,
@@ -370,6 +484,21 @@ void launch_row_rhs(const Geom& g, const RowDesign& d, const double* B, const do
 void launch_level_update(const Geom& g, bool masked, const RowDesign& d, int lfac_base, const double* G, const double* B, const double* T,
                          const double* Lfac, double* U, cudaStream_t st) {
     k_level_update<<<d.L, 128, 0, st>>>(g.K, g.KP, masked ? 1 : 0, d.rows_sorted, d.level_start, d.A, G, B, T, Lfac, lfac_base, U);
+}
+
+void launch_level_sumB(const Geom& g, const LevelTable* tab_dev, int total_levels, const double* B, double* SB, cudaStream_t st) {
+    if (total_levels) k_level_sumB<<<total_levels, 128, 0, st>>>(tab_dev, g.KP, B, SB);
+}
+
+void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, double* A_all, const double* W, const double* SB,
+                          const double* G, const double* Lfac, cudaStream_t st) {
+    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0};
+    const size_t FK = (size_t)g.KP * g.KP + g.KP, limit = 227 * 1024;
+    size_t smem = ((size_t)g.KP * g.KP + GS_WARPS * FK) * 8;
+    if (smem + (size_t)total_levels * g.KP * 8 <= limit) { a.a_in_smem = 1; smem += (size_t)total_levels * g.KP * 8; }
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_rows_dense_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit); attr_set = true; }
+    k_rows_dense_gs<<<GS_CLUSTER, GS_WARPS * 32, smem, st>>>(a);
 }
 
 size_t continuous_scratch_elems(const Geom& g) { return (size_t)((g.N + 63) / 64) * (g.KP * g.KP + g.KP); }

@@ -97,7 +97,11 @@ struct insider_resident {
     uint32_t *trC = nullptr, *teC = nullptr, *trR = nullptr;
     std::vector<int> L;
     std::vector<int*> level_of_row, rows_sorted, level_start;
-    std::vector<std::vector<int>> level_start_host;
+    std::vector<std::vector<int>> level_start_host, lor_host;
+    // dense-path Gauss-Seidel tables (design only): co-occurrence CSR over all levels, per-level sums of X
+    int total_levels = 0;
+    int *gs_lvl_first = nullptr, *gs_co_ptr = nullptr, *gs_co_row = nullptr;
+    double *gs_co_cnt = nullptr, *gs_Sx = nullptr;
     double n_train = 0, n_test = 0;
     double h2d_bytes = 0;
     DevPool pool;
@@ -126,6 +130,7 @@ struct insider_session {
     int total_levels = 0, max_chunks = 1;
     LevelTable* tab_dev = nullptr;
     double* Lfac = nullptr;             // [total_levels][KP*KP + KP] Cholesky factors + inverse diagonals
+    double* SB = nullptr;               // dense path: [total_levels][KP] per-level sums of B
     int rb_splits = 1, d_splits = 1, stream_blocks = 1;
     RowDesign* designs_dev = nullptr;
     std::vector<RowDesign> designs;
@@ -229,7 +234,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
             CUDA_TRY(cudaMemcpyAsync(d_sorted, sorted.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d_start, start.data(), (L + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));   // host vectors go out of scope
-            r->level_start_host.push_back(start);
+            r->level_start_host.push_back(start); r->lor_host.push_back(lor);
             r->L.push_back(L); r->level_of_row.push_back(d_lor); r->rows_sorted.push_back(d_sorted); r->level_start.push_back(d_start);
             r->h2d_bytes += (2.0 * N + L + 1) * 4;
         }
@@ -237,6 +242,41 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
             r->X = r->pool.get<double>((size_t)N * r->Q, false);
             CUDA_TRY(cudaMemcpyAsync(r->X, pb->X, (size_t)N * r->Q * 8, cudaMemcpyHostToDevice, st));
             r->h2d_bytes += (double)N * r->Q * 8;
+        }
+        // dense-path tables: for every level (c, s) the co-occurring levels (c' != c, s') with their sample counts
+        {
+            std::vector<int> first(r->C + 1, 0);
+            for (int c = 0; c < r->C; ++c) first[c + 1] = first[c] + r->L[c];
+            r->total_levels = first[r->C];
+            std::vector<int> ptr(r->total_levels + 1, 0), rows;
+            std::vector<double> cnts, Sx((size_t)std::max(1, r->total_levels) * std::max(1, r->Q), 0.0);
+            for (int c = 0; c < r->C; ++c)
+                for (int l = 0; l < r->L[c]; ++l) {
+                    std::map<int, int> co;
+                    const int b = r->level_start_host[c][l], e = r->level_start_host[c][l + 1];
+                    std::vector<int> members;
+                    for (int k = 0; k < N; ++k) if (r->lor_host[c][k] == l) members.push_back(k);
+                    (void)b; (void)e;
+                    for (int k : members) {
+                        for (int c2 = 0; c2 < r->C; ++c2) if (c2 != c) co[first[c2] + r->lor_host[c2][k]] += 1;
+                        for (int q = 0; q < r->Q; ++q) Sx[(size_t)(first[c] + l) * r->Q + q] += pb->X[(size_t)q * N + k];
+                    }
+                    for (auto& kv : co) { rows.push_back(kv.first); cnts.push_back((double)kv.second); }
+                    ptr[first[c] + l + 1] = (int)rows.size();
+                }
+            r->gs_lvl_first = r->pool.get<int>(first.size(), false);
+            r->gs_co_ptr = r->pool.get<int>(ptr.size(), false);
+            r->gs_co_row = r->pool.get<int>(std::max<size_t>(1, rows.size()), false);
+            r->gs_co_cnt = r->pool.get<double>(std::max<size_t>(1, cnts.size()), false);
+            r->gs_Sx = r->pool.get<double>(Sx.size(), false);
+            CUDA_TRY(cudaMemcpyAsync(r->gs_lvl_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(r->gs_co_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice, st));
+            if (!rows.empty()) {
+                CUDA_TRY(cudaMemcpyAsync(r->gs_co_row, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(r->gs_co_cnt, cnts.data(), cnts.size() * 8, cudaMemcpyHostToDevice, st));
+            }
+            CUDA_TRY(cudaMemcpyAsync(r->gs_Sx, Sx.data(), Sx.size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
         }
         // masks -> bit planes
         if (r->has_masks) {
@@ -389,10 +429,21 @@ void run_iteration(insider_session* s) {
         { Launch l(s, "k_level_factor"); launch_level_factor(g, s->masked, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, st); }
     }
     // Gauss-Seidel over confounder blocks (:335-362)
-    for (int c = 0; c < r->C; ++c) {
-        const RowDesign& d = s->designs[c];
-        if (s->masked) { Launch l(s, "k_row_rhs"); launch_row_rhs(g, d, s->B, s->G, s->D, s->U, s->T, st); }
-        { Launch l(s, "k_level_update"); launch_level_update(g, s->masked, d, s->lfac_base[c], s->G, s->B, s->T, s->Lfac, s->U, st); }
+    if (s->masked) {
+        for (int c = 0; c < r->C; ++c) {
+            const RowDesign& d = s->designs[c];
+            { Launch l(s, "k_row_rhs"); launch_row_rhs(g, d, s->B, s->G, s->D, s->U, s->T, st); }
+            { Launch l(s, "k_level_update"); launch_level_update(g, true, d, s->lfac_base[c], s->G, s->B, s->T, s->Lfac, s->U, st); }
+        }
+    } else if (r->C > 0) {
+        // dense path: per-level sums of B once, then all C block updates in one single-block launch on factor-sized data
+        DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
+        { Launch l(s, "k_level_sumB"); launch_level_sumB(g, s->tab_dev, s->total_levels, s->B, s->SB, st); }
+        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs(g, dg, r->C, r->Q, s->total_levels, s->A_all, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->SB, s->G, s->Lfac, st); }
+        if (r->inc_continuous) {   // the continuous block below works on the row factor: rebuild it with the new A_c
+            Launch l(s, "k_build_u", 2);
+            launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, s->A_all + s->a_off[r->C], s->U, s->Ut, s->UtU, st);
+        }
     }
     if (r->inc_continuous) {
         double* W = s->A_all + s->a_off[r->C];
@@ -470,6 +521,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             if (!tab.empty()) CUDA_TRY(cudaMemcpyAsync(s->tab_dev, tab.data(), tab.size() * sizeof(LevelTable), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             s->Lfac = s->pool.get<double>((size_t)std::max(1, s->total_levels) * (KK + g.KP), true, st);
+            s->SB = s->pool.get<double>((size_t)std::max(1, s->total_levels) * g.KP, true, st);
         }
         if (s->masked) {
             s->d_splits = std::max(1, std::min(16, (ctx->sm_count * 16 + g.N - 1) / g.N));

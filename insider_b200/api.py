@@ -146,8 +146,14 @@ def _resident_for(obj, ctx, masks=True):
     return ctx.upload(prob)
 
 
-def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None, write_csv=True):
-    """reference R/insider.R:81-176. Returns dict(rank_tuning, latent_rank, reg_tuning)."""
+def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None, ctxs=None, write_csv=True):
+    """reference R/insider.R:81-176. Returns dict(rank_tuning, latent_rank, reg_tuning).
+
+    Grid points are independent fits. With ``ctxs`` (a list of contexts, e.g. one per GPU) the points of each phase are
+    run as replicas, one host thread per context, every context holding its own resident copy of the data — no
+    communication. Each point draws its initial factors from a generator seeded by (seed, phase, point index), so the
+    results do not depend on how points are scheduled (the reference uses whatever R's RNG stream holds at that moment).
+    """
     ld = np.atleast_1d(latent_dimension) if latent_dimension is not None else np.array([], dtype=int)
     lam = np.atleast_1d(np.asarray(lambda_, dtype=float))
     alp = np.atleast_1d(np.asarray(alpha, dtype=float))
@@ -155,44 +161,57 @@ def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None
         raise ValueError("TUNNING: The element of latent_dimension, lambda, and alpha should be integer, numeric, and numeric.")
     if len(ld) <= 1 and (len(lam) <= 1 and len(alp) <= 1):
         raise ValueError("TUNNING: The length of either latent_dimension or lambda and alpha should be greater than 1.")
-    ctx = ctx or default_context()
+    ctx_list = list(ctxs) if ctxs else [ctx or default_context()]
     p = obj["params"]
-    rng = np.random.default_rng(seed)
-    res = _resident_for(obj, ctx)                                 # the 51 fits share one upload
+    residents = [_resident_for(obj, c) for c in ctx_list]       # all fits of a context share one upload
+
+    def run_points(phase, points):
+        """points: list of (K, lambda1, lambda2, alpha); returns the fitted dicts in order."""
+        out = [None] * len(points)
+
+        def work(slot):
+            for i in range(slot, len(points), len(ctx_list)):
+                K, l1, l2, a = points[i]
+                flist, V = _init_factors(obj, int(K), np.random.default_rng([seed, phase, i]))
+                out[i] = optimize(None, flist, V, None, None, None, None, obj["inc_continuous"], int(K), l1, l2, a, 1, p["global_tol"],
+                                  p["sub_tol"], p["tuning_iter"], seed=seed, ctx=ctx_list[slot], resident=residents[slot])
+        if len(ctx_list) == 1:
+            work(0)
+        else:
+            import concurrent.futures as cf
+            with cf.ThreadPoolExecutor(len(ctx_list)) as ex:
+                list(ex.map(work, range(len(ctx_list))))
+        return out
+
     rank_tuning, reg_tuning = None, None
     try:
         if len(ld) > 1:                                           # :98-132
-            rows = []
-            for latent_rank in ld:
-                print("Latent rank: ", latent_rank, "---------------------------------")
-                flist, V = _init_factors(obj, int(latent_rank), rng)
-                if len(lam) == 1 and len(alp) == 1:
-                    l1, l2, a = float(lam[0]), float(lam[0]), float(alp[0])
-                else:
-                    l1, l2, a = 0.1, 0.1, 0.0                     # :120-121
-                fitted = optimize(None, flist, V, None, None, None, None, obj["inc_continuous"], int(latent_rank), l1, l2, a, 1,
-                                  p["global_tol"], p["sub_tol"], p["tuning_iter"], seed=seed, ctx=ctx, resident=res)
-                rows.append([latent_rank, fitted["train_rmse"], fitted["test_rmse"]])
-                rank_tuning = np.array(rows, dtype=float)
-                if write_csv:
-                    np.savetxt("insider_rank_tuning_result.csv", rank_tuning, delimiter=",", header="rank,train_rmse,test_rmse", comments="")
+            if len(lam) == 1 and len(alp) == 1:
+                pts = [(int(k), float(lam[0]), float(lam[0]), float(alp[0])) for k in ld]
+            else:
+                pts = [(int(k), 0.1, 0.1, 0.0) for k in ld]       # :120-121
+            for k in ld:
+                print("Latent rank: ", k, "---------------------------------")
+            fitted = run_points(0, pts)
+            rank_tuning = np.array([[pt[0], f["train_rmse"], f["test_rmse"]] for pt, f in zip(pts, fitted)], dtype=float)
+            if write_csv:
+                np.savetxt("insider_rank_tuning_result.csv", rank_tuning, delimiter=",", header="rank,train_rmse,test_rmse", comments="")
         latent_rank = int(ld[np.argmin(rank_tuning[:, 2])]) if len(ld) > 1 else int(ld[0])   # :135-139
         if len(lam) > 1 or len(alp) > 1:                          # :142-174, expand.grid: lambda varies fastest
-            rows = []
+            pts = []
             for a0 in alp:
                 for l0 in lam:
                     l, a = round(float(l0), 2), round(float(a0), 2)
                     print("parameter grid:", f"{l},{a}", "---------------------------------")
-                    flist, V = _init_factors(obj, latent_rank, rng)
-                    fitted = optimize(None, flist, V, None, None, None, None, obj["inc_continuous"], latent_rank, l, l, a, 1,
-                                      p["global_tol"], p["sub_tol"], p["tuning_iter"], seed=seed, ctx=ctx, resident=res)
-                    rows.append([l, a, fitted["train_rmse"], fitted["test_rmse"]])
-                    reg_tuning = np.array(rows, dtype=float)
-                    if write_csv:
-                        np.savetxt(f"insider_R{latent_rank}_reg_tuning_result.csv", reg_tuning, delimiter=",",
-                                   header="lambda,alpha,train_rmse,test_rmse", comments="")
+                    pts.append((latent_rank, l, l, a))
+            fitted = run_points(1, pts)
+            reg_tuning = np.array([[pt[1], pt[3], f["train_rmse"], f["test_rmse"]] for pt, f in zip(pts, fitted)], dtype=float)
+            if write_csv:
+                np.savetxt(f"insider_R{latent_rank}_reg_tuning_result.csv", reg_tuning, delimiter=",", header="lambda,alpha,train_rmse,test_rmse",
+                           comments="")
     finally:
-        res.release()
+        for r in residents:
+            r.release()
     return dict(rank_tuning=rank_tuning, latent_rank=latent_rank, reg_tuning=reg_tuning)
 
 

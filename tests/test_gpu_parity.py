@@ -257,6 +257,12 @@ def test_api_mirror_insider_tune_fit(ctx, tmp_path, monkeypatch):
     assert t["rank_tuning"].shape == (2, 3) and t["reg_tuning"].shape == (4, 4) and t["latent_rank"] in (2, 4)
     assert t["reg_tuning"][:, 0].tolist() == [1.0, 3.0, 1.0, 3.0]                    # expand.grid: lambda fastest
     assert os.path.exists("insider_rank_tuning_result.csv") and os.path.exists(f"insider_R{t['latent_rank']}_reg_tuning_result.csv")
+    # replicas: the same grid spread over two contexts (threads) gives identical numbers
+    from insider_b200 import _cabi as cabi
+    ctx2 = cabi.Context(0)
+    t2 = api.tune(obj, np.array([2, 4], dtype=np.int64), np.array([1.0, 3.0]), np.array([0.2, 0.4]), seed=1, ctxs=[ctx, ctx2], write_csv=False)
+    ctx2.close()
+    assert np.array_equal(t2["rank_tuning"], t["rank_tuning"]) and np.array_equal(t2["reg_tuning"], t["reg_tuning"])
     obj = api.fit(obj, 4, 3.0, 0.4, partition=0, seed=2)
     assert sorted(obj["cfd_matrices"]) == [f"factor{i}" for i in range(obj["confounder"].shape[1])]
     assert obj["column_factor"].shape == (4, 150) and np.isnan(obj["test_rmse"])

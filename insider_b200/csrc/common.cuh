@@ -66,6 +66,19 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Copies n doubles global -> shared with a warp/group of `nthr` threads (thread index `t`), eight independent loads in
+// flight per thread: a plain `for (x = t; x < n; x += nthr) dst[x] = src[x]` loop issues its loads one latency at a time.
+__device__ __forceinline__ void copy_batched(double* dst, const double* __restrict__ src, int n, int t, int nthr) {
+    int x = t;
+    for (; x + 7 * nthr < n; x += 8 * nthr) {
+        const double v0 = src[x], v1 = src[x + nthr], v2 = src[x + 2 * nthr], v3 = src[x + 3 * nthr];
+        const double v4 = src[x + 4 * nthr], v5 = src[x + 5 * nthr], v6 = src[x + 6 * nthr], v7 = src[x + 7 * nthr];
+        dst[x] = v0; dst[x + nthr] = v1; dst[x + 2 * nthr] = v2; dst[x + 3 * nthr] = v3;
+        dst[x + 4 * nthr] = v4; dst[x + 5 * nthr] = v5; dst[x + 6 * nthr] = v6; dst[x + 7 * nthr] = v7;
+    }
+    for (; x < n; x += nthr) dst[x] = src[x];
+}
+
 // FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col). Lane l: g = l>>2, t = l&3.
 //   a = A[g][t], b = B[t][g], d0 = D[g][2t], d1 = D[g][2t+1].
 // Measured on B200 (profiles/r01_microbench_fp64_hbm.txt): result == fma(a3,b3,fma(a2,b2,fma(a1,b1,fma(a0,b0,c)))).

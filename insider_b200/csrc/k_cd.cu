@@ -212,10 +212,21 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
             } else {
                 gene = (int64_t)jn;
                 if (PERGENE) {
+                    // per-gene matrix global -> shared, eight independent loads in flight per lane (a plain strided loop
+                    // pays one L2 round trip per element: 72 of them per gene)
                     const double* src = a.Xall + (size_t)gene * a.x_stride;
-                    for (int x = li; x < KP * KP; x += LPG) {
-                        const int r = x / KP, c = x % KP;
-                        Xs[r * XLD + c] = (r < K && c < K) ? src[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;
+                    for (int x0 = li; x0 < KP * KP; x0 += 8 * LPG) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int x = x0 + u * LPG, r = x / KP, c = x % KP;
+                            v[u] = (x < KP * KP && r < K && c < K) ? src[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int x = x0 + u * LPG;
+                            if (x < KP * KP) Xs[(x / KP) * XLD + (x % KP)] = v[u];
+                        }
                     }
                     __syncwarp(gmask);
                 }
@@ -418,9 +429,15 @@ __global__ void __launch_bounds__(128) k_col_ridge(RidgeArgs a) {
         if (MASKED) {
             double* S = S0 + (size_t)warp * KP * XLD;
             const double* src = a.Xall + (size_t)j * KP * KP;
-            for (int x = lane; x < KP * KP; x += 32) {
-                const int r = x / KP, c = x % KP;
-                S[r * XLD + c] = src[x] + ((r == c) ? a.lambda : 0.0);             // :225
+            for (int x0 = lane; x0 < KP * KP; x0 += 8 * 32) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int x = x0 + u * 32; v[u] = (x < KP * KP) ? src[x] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int x = x0 + u * 32, r = x / KP, c = x % KP;
+                    if (x < KP * KP) S[r * XLD + c] = v[u] + ((r == c) ? a.lambda : 0.0);   // :225
+                }
             }
             __syncwarp();
             ok = warp_chol_factor(S, XLD, a.K, lane);

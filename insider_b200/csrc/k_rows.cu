@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) k_level_update(int K, int KP, int masked,
     if (e == b) return;
     {
         const double* src = Lfac + (size_t)(lfac_base + s) * (KP * KP + KP);
-        for (int x = threadIdx.x; x < KP * KP + KP; x += 128) Lf_s[x] = src[x];
+        copy_batched(Lf_s, src, KP * KP + KP, threadIdx.x, 128);
     }
     double p0 = 0.0, p1 = 0.0;     // masked: p0 = sum T ; dense: p0 = sum B, p1 = sum u
     const double* src0 = masked ? T : B;
@@ -294,12 +294,22 @@ __global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 
     const double* Asrc = a.a_in_smem ? As : a.A_all;
     for (int c = 0; c < a.C; ++c) {                                            // src/optimize.cpp:335 (fixed block order)
         // (re)load the factors: blocks updated earlier in this sweep were written by other CTAs of the cluster
-        if (a.a_in_smem) for (int x = threadIdx.x; x < n_lv * KP; x += blockDim.x) As[x] = __ldcg(a.A_all + x);
+        if (a.a_in_smem) {
+            // __ldcg semantics are not needed for correctness of plain loads here: the data was written before a cluster.sync
+            // (release/acquire at cluster scope) and As is refilled after it; L1 holds no stale copy because A_all is only
+            // ever read through this staging copy.
+            int x = threadIdx.x; const int nthr = blockDim.x, n = n_lv * KP;
+            for (; x + 3 * nthr < n; x += 4 * nthr) {
+                const double v0 = __ldcg(a.A_all + x), v1 = __ldcg(a.A_all + x + nthr), v2 = __ldcg(a.A_all + x + 2 * nthr), v3 = __ldcg(a.A_all + x + 3 * nthr);
+                As[x] = v0; As[x + nthr] = v1; As[x + 2 * nthr] = v2; As[x + 3 * nthr] = v3;
+            }
+            for (; x < n; x += nthr) As[x] = __ldcg(a.A_all + x);
+        }
         __syncthreads();
         for (int lv = a.lvl_first[c] + gw; lv < a.lvl_first[c + 1]; lv += n_gw) {
             // stage this level's Cholesky factor (independent loads, issued before anything depends on them)
             const double* Lf = a.Lfac + (size_t)lv * FK;
-            for (int x = lane; x < FK; x += 32) Lw[x] = Lf[x];
+            copy_batched(Lw, Lf, FK, lane, 32);
             // w = sum over co-occurring levels of count * a_{c',s'}: 32 CSR entries per batch, broadcast by shuffle
             double w = 0.0;
             const int e0 = a.co_ptr[lv], e1 = a.co_ptr[lv + 1];

@@ -23,31 +23,39 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-__host__ __device__ inline uint64_t perm_key(uint64_t seed, uint32_t als_iter, uint64_t gene, uint32_t draw) {
-    return mix64(seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter)) ^
-           mix64(gene * 0xD1B54A32D192ED03ull + (uint64_t)draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+// Key of sweep `draw` of a gene's solve in ALS iteration `als_iter`. The gene is NOT part of the key: every gene at the same
+// sweep index shares the visiting order (each gene still sees a fresh uniformly random order per sweep), which makes the
+// coordinate warp-uniform in the thread-per-gene solver (k_cd_dense.cu).
+__host__ __device__ inline uint64_t perm_key(uint64_t seed, uint32_t als_iter, uint32_t draw) {
+    return mix64(seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter)) ^ mix64((uint64_t)draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
 }
 __host__ __device__ inline uint32_t perm_value(uint64_t key, int pos) {
     return (uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(pos + 1)) >> 38);   // 26-bit sort key
 }
-// Permutation table: for every size n = 1..32, PERM_T permutations, each built like arma::randperm (sort n random
-// keys ascending, ties by index). rank_table[((n-1)*PERM_T + t)*32 + p] = position of element p in the visiting order.
-// A sweep selects t = perm_select(perm_key(seed, als_iter, gene, draw)). Identical in oracle/insider_oracle.cpp.
+// Permutation tables: for every size n = 1..32, PERM_T permutations, each built like arma::randperm (sort n random
+// keys ascending, ties by index). A sweep selects t = perm_select(perm_key(seed, als_iter, draw)) with n = K (all
+// coordinates); a gene visits its active coordinates in that order. Identical in oracle/insider_oracle.cpp.
+//   rank table : table[((n-1)*PERM_T + t)*32 + p]                = position of coordinate p in the visiting order
+//   order table: table[PERM_TABLE_HALF + ((n-1)*PERM_T + t)*32 + i] = coordinate visited at position i
 constexpr int PERM_T = 4096;
 constexpr int PERM_NMAX = 32;
+constexpr size_t PERM_TABLE_HALF = (size_t)PERM_NMAX * PERM_T * 32;
+constexpr size_t PERM_TABLE_BYTES = 2 * PERM_TABLE_HALF;
 __host__ __device__ inline uint64_t perm_table_key(int n, int t) { return mix64(0x1F83D9ABFB41BD6Bull ^ (((uint64_t)n << 32) | (uint64_t)t)); }
 __host__ __device__ inline uint32_t perm_select(uint64_t pk) { return (uint32_t)(pk >> 20) & (uint32_t)(PERM_T - 1); }
-inline void build_perm_table(unsigned char* table /* [PERM_NMAX * PERM_T * 32] */) {
+inline void build_perm_table(unsigned char* table /* [PERM_TABLE_BYTES] */) {
     for (int n = 1; n <= PERM_NMAX; ++n)
         for (int t = 0; t < PERM_T; ++t) {
             const uint64_t key = perm_table_key(n, t);
             uint32_t v[PERM_NMAX];
             for (int p = 0; p < n; ++p) v[p] = perm_value(key, p);
             unsigned char* row = table + ((size_t)(n - 1) * PERM_T + t) * 32;
+            unsigned char* ord = row + PERM_TABLE_HALF;
             for (int p = 0; p < 32; ++p) {
                 int r = 0;
                 if (p < n) { for (int m = 0; m < n; ++m) r += (v[m] < v[p]) || (v[m] == v[p] && m < p); } else r = p;
                 row[p] = (unsigned char)r;
+                ord[r] = (unsigned char)p;
             }
         }
 }

@@ -155,7 +155,7 @@ struct CdArgs {
     uint64_t seed; int perm_mode;
     unsigned long long* sweeps_total; unsigned long long* steps_total; int* sweeps_per_gene;
     unsigned int* queue;          // atomic gene counter (zeroed before launch)
-    const unsigned char* perm_table;   // [32][PERM_T][32] rank tables (common.cuh)
+    const unsigned char* perm_table;   // rank + order tables (common.cuh)
 };
 
 // persistent elastic-net solver: every 8-lane group repeatedly claims a gene, solves it, writes it back
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     bool active = false, retired = false;
     uint32_t inc = 0, draw = 0;
     int n_inc = 0, sweeps = 0;
-    uint32_t row_w = 0, row_draw = 0; int row_n = -1;          // prefetched permutation-table word (see below)
+    uint32_t row_w = 0, row_draw = 0xffffffffu;                // prefetched permutation-table word (see below)
     unsigned long long sweeps_acc = 0, steps_acc = 0;
 
     while (true) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     Bc[c] = beta[s]; Qc[c] = q[s]; Dc[c] = d; DENc[c] = den; RDc[c] = 1.0 / den;
                 }
                 __syncwarp(gmask);
-                n_inc = __popc(inc); draw = 0; sweeps = 0; active = true; row_n = -1;
+                n_inc = __popc(inc); draw = 0; sweeps = 0; active = true; row_draw = 0xffffffffu;
             }
         }
         if (__all_sync(FULL, retired)) break;
@@ -278,23 +278,33 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         //      the permutation selected from the table by the per-sweep key; inactive ones keep ascending order behind them.
         int pos[SL];
         {
-            // lane li holds 4-byte word li of the 32-byte rank row; the row of the NEXT sweep is prefetched one sweep ahead
+            // The per-sweep key selects a table permutation of all K coordinates (shared by every gene at this sweep index);
+            // lane li holds 4-byte word li of its 32-byte rank row. The row of the NEXT sweep is prefetched one sweep ahead.
             auto row_word = [&](uint32_t dr) -> const uint32_t* {
-                const uint64_t pk = key_iter ^ mix64((uint64_t)(a.gene0 + gene) * 0xD1B54A32D192ED03ull + (uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
-                return reinterpret_cast<const uint32_t*>(a.perm_table + ((size_t)(max(n_inc, 1) - 1) * PERM_T + perm_select(pk)) * 32) + li;
+                const uint64_t pk = key_iter ^ mix64((uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+                return reinterpret_cast<const uint32_t*>(a.perm_table + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + li;
             };
-            if (row_n != n_inc || row_draw != draw) row_w = __ldg(row_word(draw));       // new gene or changed active set
+            if (row_draw != draw) row_w = __ldg(row_word(draw));                          // new gene
+            // rank of every own coordinate in the full order; A = set of ranks taken by active coordinates
+            int rk[SL];
+            uint32_t A = 0;
+#pragma unroll
+            for (int s = 0; s < SL; ++s) {
+                const int c = s * LPG + li;
+                const uint32_t w = __shfl_sync(FULL, row_w, c >> 2, LPG);
+                rk[s] = (a.perm_mode == 1) ? (int)((w >> (8 * (c & 3))) & 0xffu) : c;
+                if ((inc >> c) & 1u) A |= 1u << rk[s];
+            }
+            A |= __shfl_xor_sync(FULL, A, 4); A |= __shfl_xor_sync(FULL, A, 2); A |= __shfl_xor_sync(FULL, A, 1);
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 const int c = s * LPG + li;
                 const uint32_t below = (1u << c) - 1u;
-                const int p_act = __popc(inc & below) & 31;
                 const bool on = (inc >> c) & 1u;
-                const uint32_t w = __shfl_sync(FULL, row_w, p_act >> 2, LPG);
-                const int p_perm = (a.perm_mode == 1) ? (int)((w >> (8 * (p_act & 3))) & 0xffu) : p_act;
-                pos[s] = on ? p_perm : ((c < K) ? n_inc + __popc(~inc & valid_mask & below) : c);
+                // active: rank among the active coordinates; inactive ones keep ascending order behind them
+                pos[s] = on ? __popc(A & ((1u << rk[s]) - 1u)) : ((c < K) ? n_inc + __popc(~inc & valid_mask & below) : c);
             }
-            row_w = __ldg(row_word(draw + 1)); row_n = n_inc; row_draw = draw + 1;       // consumed by the next sweep
+            row_w = __ldg(row_word(draw + 1)); row_draw = draw + 1;                       // consumed by the next sweep
         }
         ++draw;
         __syncwarp();

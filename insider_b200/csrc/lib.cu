@@ -457,7 +457,13 @@ void run_iteration(insider_session* s) {
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
-    { Launch l(s, "k_col_solve"); launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st); }
+    if (!s->masked && s->opt.alpha != 0.0) {
+        Launch l(s, "k_cd_dense");
+        launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, nullptr, nullptr, s->ctx->perm_table, st);
+    } else {
+        Launch l(s, "k_col_solve");
+        launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
+    }
 }
 
 insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* f, const insider_options* o) {
@@ -661,7 +667,7 @@ int create_ctx(insider_ctx** out, int device, int rank, int world, const void* i
         try {
             CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
             {
-                std::vector<unsigned char> tab((size_t)PERM_NMAX * PERM_T * 32);
+                std::vector<unsigned char> tab(PERM_TABLE_BYTES);
                 build_perm_table(tab.data());
                 CUDA_TRY(cudaMalloc(&c->perm_table, tab.size()));
                 CUDA_TRY(cudaMemcpy(c->perm_table, tab.data(), tab.size(), cudaMemcpyHostToDevice));
@@ -818,7 +824,8 @@ int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const do
         CUDA_TRY(cudaMemcpyAsync(dG, XtX, gsz * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dx, Xty, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dw, wstart, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
-        launch_cd_batch(K, n_cols, dG, shared_gram != 0, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, dq, ctx->perm_table, ctx->sm_count, st);
+        if (shared_gram) launch_cd_dense_batch(K, n_cols, dG, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, db, dsw, ctx->perm_table, st);
+        else launch_cd_batch(K, n_cols, dG, false, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, dq, ctx->perm_table, ctx->sm_count, st);
         CUDA_TRY(cudaMemcpyAsync(beta, db, (size_t)K * n_cols * 8, cudaMemcpyDeviceToHost, st));
         if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, (size_t)n_cols * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

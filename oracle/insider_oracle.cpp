@@ -23,9 +23,12 @@
 //
 // Permutation modes for the coordinate order (coordinate_descent.cpp:89):
 //   mode 0 (A) R-stream-faithful: one global R RNG consumed gene after gene (single-thread semantics).
-//   mode 1 (B) counter-based: key (seed, als_iter, gene, draw) selects one of 4096 table permutations of the active-set
-//              size, each built like randperm (sort 26-bit random keys, index tie-break). Identical on CPU and GPU;
-//              parity at scale is defined in this mode.
+//   mode 1 (B) counter-based: key (seed, als_iter, draw) - draw = index of the sweep within the gene's solve - selects one
+//              of 4096 table permutations of all K coordinates, each built like randperm (sort 26-bit random keys, index
+//              tie-break); a gene visits its ACTIVE coordinates in that order (a uniformly random order of the active
+//              set, like randperm(|inc|)). The key does not depend on the gene, so every gene that is at sweep d of ALS
+//              iteration t uses the same order: that is what lets the GPU run one gene per thread with a warp-uniform
+//              coordinate. Identical on CPU and GPU; parity at scale is defined in this mode.
 //   mode 2     identity order (no shuffling) - for analytic tests.
 
 #include <algorithm>
@@ -104,8 +107,9 @@ struct PermSrc {
     RRng* r = nullptr;
 };
 
-// arma::randperm(n) as used at coordinate_descent.cpp:89.
-void randperm(PermSrc& ps, int n, int* ord) {
+// arma::randperm(n) as used at coordinate_descent.cpp:89: visiting order of the n = |inc| active coordinates, as indices
+// into inc (ascending list of active coordinates out of K).
+void randperm(PermSrc& ps, int n, int* ord, const int* inc = nullptr, int K = 0) {
     if (n <= 0) { ps.draw++; return; }
     std::vector<std::pair<uint32_t, int>> pk(n);
     if (ps.mode == 0) {
@@ -114,13 +118,20 @@ void randperm(PermSrc& ps, int n, int* ord) {
             pk[i] = {(uint32_t)(int)u, i};
         }
     } else if (ps.mode == 1) {
-        // mode B: the per-sweep key selects one of PERM_T table permutations of size n; every table entry is built like
-        // randperm itself (sort n 26-bit random keys ascending, ties by index) from a fixed table key.
+        // mode B: the per-sweep key selects one of PERM_T table permutations of all K coordinates; every table entry is built
+        // like randperm itself (sort K 26-bit random keys ascending, ties by index) from a fixed table key. Active coordinate
+        // inc[i] is visited at its rank among the active ones.
+        if (!inc || K <= 0) K = n;
         const uint64_t sel = mix64(ps.seed + 0x9E3779B97F4A7C15ull * (1ull + ps.als_iter)) ^
-                            mix64(ps.gene * 0xD1B54A32D192ED03ull + (uint64_t)ps.draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+                            mix64((uint64_t)ps.draw * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
         const uint64_t t = (sel >> 20) & 4095ull;
-        const uint64_t key = mix64(0x1F83D9ABFB41BD6Bull ^ (((uint64_t)n << 32) | t));
-        for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1)) >> 38), i};
+        const uint64_t key = mix64(0x1F83D9ABFB41BD6Bull ^ (((uint64_t)K << 32) | t));
+        std::vector<std::pair<uint32_t, int>> full(K);
+        for (int c = 0; c < K; ++c) full[c] = {(uint32_t)(mix64(key + 0x9E3779B97F4A7C15ull * (uint64_t)(c + 1)) >> 38), c};
+        std::stable_sort(full.begin(), full.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        std::vector<int> rank(K);
+        for (int i = 0; i < K; ++i) rank[full[i].second] = i;
+        for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)rank[inc ? inc[i] : i], i};
     } else {
         for (int i = 0; i < n; ++i) pk[i] = {(uint32_t)i, i};
     }
@@ -173,6 +184,9 @@ double compute_loss_vec(int n, const double* r, int K, const double* beta, doubl
 
 struct CdStats { int sweeps = 0; int rounds = 0; };
 
+// optional per-gene sweep-count sink (diagnostics for tools/): g_sweep_sink[als_iter * P + gene]
+int* g_sweep_sink = nullptr; long long g_sweep_sink_len = 0;
+
 // src/coordinate_descent.cpp:57-127  strong_coordinate_descent()
 // X is n x K column-major (the rows of the row factor selected for this gene), y the selected outcomes.
 void strong_cd(int n, int K, const double* X, const double* y, const double* wstart, double lambda, double alpha,
@@ -194,7 +208,7 @@ void strong_cd(int n, int K, const double* X, const double* y, const double* wst
         for (int k = 0; k < K; ++k) (active[k] ? inc : ex).push_back(k);                // :83-84
         do {
             pre_loss = iter_loss;                                                       // :87
-            randperm(ps, (int)inc.size(), ord.data());                                  // :89
+            randperm(ps, (int)inc.size(), ord.data(), inc.data(), K);                   // :89
             for (size_t i = 0; i < inc.size(); ++i) {
                 const int k = inc[ord[i]];                                              // :92
                 const double* xk = X + (size_t)k * n;
@@ -414,6 +428,7 @@ int optimize_col(const Problem& pb, const double* U /*N x K col-major*/, double*
                 strong_cd(n, K, feature.data(), outcome.data(), vj, lambda, alpha, XtX.data(), Xty.data(), tol, ps, beta.data(), &st);
                 for (int a = 0; a < K; ++a) vj[a] = beta[a];
                 sweeps += st.sweeps;
+                if (g_sweep_sink && (long long)als_iter * P + j < g_sweep_sink_len) g_sweep_sink[(size_t)als_iter * P + j] = st.sweeps;
             }
         }
     } else {
@@ -437,6 +452,7 @@ int optimize_col(const Problem& pb, const double* U /*N x K col-major*/, double*
                 strong_cd(N, K, U, yj, vj, lambda, alpha, gram.data(), Xty.data(), tol, ps, beta.data(), &st);
                 for (int a = 0; a < K; ++a) vj[a] = beta[a];
                 sweeps += st.sweeps;
+                if (g_sweep_sink && (long long)als_iter * P + j < g_sweep_sink_len) g_sweep_sink[(size_t)als_iter * P + j] = st.sweeps;
             }
         }
     }
@@ -554,6 +570,7 @@ struct oracle_check {
 };
 
 int oracle_version(void) { return 1; }
+void oracle_set_sweep_sink(int* buf, long long len) { g_sweep_sink = buf; g_sweep_sink_len = len; }
 
 // src/coordinate_descent.cpp:57-127 — single-column entry (KATs).
 int oracle_strong_cd(int n, int K, const double* X, const double* y, const double* wstart, double lambda, double alpha,
@@ -572,6 +589,11 @@ int oracle_strong_cd(int n, int K, const double* X, const double* y, const doubl
 void oracle_randperm_b(uint64_t seed, uint32_t als_iter, uint64_t gene, uint32_t draw, int n, int* ord) {
     PermSrc ps; ps.mode = 1; ps.seed = seed; ps.als_iter = als_iter; ps.gene = gene; ps.draw = draw;
     randperm(ps, n, ord);
+}
+// the same restricted to an active set: inc = ascending active coordinates out of K; ord = visiting order as indices into inc
+void oracle_randperm_b_inc(uint64_t seed, uint32_t als_iter, uint32_t draw, int K, const int* inc, int n_inc, int* ord) {
+    PermSrc ps; ps.mode = 1; ps.seed = seed; ps.als_iter = als_iter; ps.draw = draw;
+    randperm(ps, n_inc, ord, inc, K);
 }
 
 // src/optimize.cpp:256-422  optimize()

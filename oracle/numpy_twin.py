@@ -20,7 +20,8 @@ def compute_loss(residual, beta, lam, alpha):
 
 
 def strong_coordinate_descent(X, y, wstart, lam, alpha, XtX, Xty, tol=1e-5, perm=None, stats=None):
-    """src/coordinate_descent.cpp:57-127. ``perm(n)`` returns the visiting order of the n active coordinates."""
+    """src/coordinate_descent.cpp:57-127. ``perm(inc_idx, K)`` returns the visiting order of the active coordinates
+    (indices into ``inc_idx``)."""
     beta = np.array(wstart, dtype=float)
     K = beta.size
     active = np.ones(K)
@@ -35,7 +36,7 @@ def strong_coordinate_descent(X, y, wstart, lam, alpha, XtX, Xty, tol=1e-5, perm
         ex_idx = np.flatnonzero(active == 0)
         while True:
             pre_loss = iter_loss
-            order = perm(inc_idx.size) if perm is not None else np.arange(inc_idx.size)
+            order = perm(inc_idx, K) if perm is not None else np.arange(inc_idx.size)
             for i in range(inc_idx.size):
                 k = inc_idx[order[i]]
                 upper = residual @ X[:, k] + beta[k] * XtX[k, k]                          # :94
@@ -203,14 +204,14 @@ def optimize(data, cfd_factors, column_factor, cfd_indicators, ctns_confounder, 
         def perm_for_gene(j, it=it):
             state = {"draw": 0}
 
-            def perm(n):
+            def perm(inc_idx, K):
                 d = state["draw"]
                 state["draw"] += 1
                 if perm_mode == 0:
-                    return rstream.randperm(n)
+                    return rstream.randperm(inc_idx.size)
                 if perm_mode == 1:
-                    return randperm_b(seed, it, j, d, n)
-                return np.arange(n)
+                    return randperm_b(seed, it, j, d, K, inc_idx)
+                return np.arange(inc_idx.size)
             return perm
 
         optimize_col(data, M, U, V, lambda2, alpha, tuning, sub_tol * decay, perm_for_gene, stats)

@@ -119,6 +119,13 @@ def randperm_b(seed, als_iter, gene, draw, n):
     return out
 
 
+def randperm_b_inc(seed, als_iter, draw, K, inc):
+    inc = np.ascontiguousarray(inc, dtype=np.int32)
+    out = np.empty(inc.size, dtype=np.int32)
+    lib().oracle_randperm_b_inc(C.c_uint64(seed), C.c_uint32(als_iter), C.c_uint32(draw), C.c_int(K), _ip(inc), C.c_int(inc.size), _ip(out))
+    return out
+
+
 def randperm_r(r_seed, n):
     out = np.empty(n, dtype=np.int32)
     lib().oracle_randperm_r(C.c_uint32(r_seed), C.c_int(n), _ip(out))

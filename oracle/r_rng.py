@@ -170,8 +170,12 @@ def ratio_splitter(data: np.ndarray, ratio: float = 0.1, rm_na_col: bool = True,
     }
 
 
-def randperm_b(seed: int, als_iter: int, gene: int, draw: int, n: int) -> np.ndarray:
-    """Counter-based permutation (mode B) — the NumPy statement of oracle/insider_oracle.cpp:randperm."""
+def randperm_b(seed: int, als_iter: int, gene: int, draw: int, n: int, inc=None) -> np.ndarray:
+    """Counter-based permutation (mode B) — the NumPy statement of oracle/insider_oracle.cpp:randperm.
+
+    The key (seed, als_iter, draw) selects a table permutation of all ``n`` coordinates (``gene`` is not part of the key:
+    every gene at sweep ``draw`` shares the order). With ``inc`` (ascending active coordinates out of n) the result is the
+    visiting order of the active set as indices into ``inc``."""
     m64 = (1 << 64) - 1
 
     def mix64(z):
@@ -180,9 +184,13 @@ def randperm_b(seed: int, als_iter: int, gene: int, draw: int, n: int) -> np.nda
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m64
         return z ^ (z >> 31)
 
-    pk = mix64(seed + 0x9E3779B97F4A7C15 * (1 + als_iter)) ^ mix64(
-        gene * 0xD1B54A32D192ED03 + draw * 0x8CB92BA72F3D8DD7 + 0x2545F4914F6CDD1D)
+    pk = mix64(seed + 0x9E3779B97F4A7C15 * (1 + als_iter)) ^ mix64(draw * 0x8CB92BA72F3D8DD7 + 0x2545F4914F6CDD1D)
     t = (pk >> 20) & 4095                                     # table entry (4096 permutations per size)
     key = mix64(0x1F83D9ABFB41BD6B ^ ((n << 32) | t))
     vals = np.array([mix64(key + 0x9E3779B97F4A7C15 * (i + 1)) >> 38 for i in range(n)], dtype=np.int64)
-    return np.argsort(vals, kind="stable")
+    order = np.argsort(vals, kind="stable")
+    if inc is None:
+        return order
+    rank = np.empty(n, dtype=np.int64)
+    rank[order] = np.arange(n)
+    return np.argsort(rank[np.asarray(inc)], kind="stable")

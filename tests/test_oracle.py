@@ -65,9 +65,9 @@ def test_strong_cd_cpp_vs_twin():
         bo, sw, _ = oracle.strong_cd(X, y, 0.01 * np.ones(7), 2.0, alpha, G, b, tol=1e-7, perm_mode=1, seed=9, als_iter=4, gene=12)
         st, draw = {}, [0]
 
-        def perm(n):
+        def perm(inc_idx, K):
             d = draw[0]; draw[0] += 1
-            return randperm_b(9, 4, 12, d, n)
+            return randperm_b(9, 4, 12, d, K, inc_idx)
         bt = numpy_twin.strong_coordinate_descent(X, y, 0.01 * np.ones(7), 2.0, alpha, G, b, 1e-7, perm, st)
         np.testing.assert_allclose(bo, bt, atol=1e-13)
         assert sw == st["sweeps"]

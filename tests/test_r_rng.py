@@ -34,6 +34,14 @@ def test_counter_permutation_cpp_vs_numpy():
         a, b = oracle.randperm_b(*args), randperm_b(*args)
         assert a.tolist() == b.tolist()
         assert sorted(a.tolist()) == list(range(args[-1]))
+    # the key does not depend on the gene: every gene at the same (ALS iteration, sweep) shares the visiting order
+    assert oracle.randperm_b(5, 3, 77, 2, 23).tolist() == oracle.randperm_b(5, 3, 1234, 2, 23).tolist()
+    # restricted to an active set: the active coordinates in the order of the full permutation
+    for inc in ([0, 1, 2, 3], [2, 5, 11, 12, 20, 22], [7], list(range(23))):
+        full = randperm_b(5, 3, 0, 2, 23)
+        want = [c for c in full.tolist() if c in inc]
+        a, b = oracle.randperm_b_inc(5, 3, 2, 23, inc), randperm_b(5, 3, 0, 2, 23, inc)
+        assert [inc[i] for i in a.tolist()] == want == [inc[i] for i in b.tolist()]
 
 
 def test_product_split_is_bit_exact_with_oracle_split():

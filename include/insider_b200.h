@@ -162,6 +162,10 @@ int insider_b200_als_end(insider_session* s, const insider_factors* fac, insider
  * launch count; returns the number of distinct kernels (timing is only collected when profile != 0 at als_begin time) */
 int insider_b200_als_profile(insider_session* s, char* names, size_t names_len, double* ms, int64_t* calls, int max_entries);
 void insider_b200_set_profile(insider_ctx* ctx, int on);
+/* diagnostics: coordinate-descent sweeps every local gene needed in the last iteration (the count strong_coordinate_descent's
+ * do-while ran, src/coordinate_descent.cpp:86-114); n = number of entries of `out`, at most the context's local gene count.
+ * Returns the number of entries written (0 when the last column update was a ridge solve or the masked solver). */
+int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n);
 
 /* batched single-column elastic-net solves (src/coordinate_descent.cpp:57-127). Problem b uses XtX[b] (K x K), Xty[b] (K),
  * wstart[b] (K); X and y of the reference signature are not needed in covariance form and are accepted as NULL.

@@ -3,17 +3,24 @@
 //   replaces  optimize_col() tuning = 0 branch   src/optimize.cpp:232-248
 //             strong_coordinate_descent()        src/coordinate_descent.cpp:57-127
 //
-// Mapping: ONE GENE PER THREAD, the whole solver state (q = X'y - X'X beta and beta, 2 x KT doubles) in registers.
-// The visiting order of a sweep depends only on (seed, ALS iteration, sweep index) - common.cuh:perm_key - so all 32
-// genes of a warp start at sweep 0 together and visit the SAME coordinate k at every step: k is warp-uniform. That makes
-//   * the XtX row of the step a shared-memory broadcast (one LDS.128 wavefront serves 32 genes x 2 columns; the 8-lanes-
-//     per-gene kernel in k_cd.cu spends ~3 wavefronts per gene-coordinate and is bound by the shared-memory pipe), and
-//   * `switch (k)` a uniform branch into a block whose register indices are compile-time constants,
-// so a coordinate update is K DFMAs + a 6-deep FP64 chain per thread and the kernel runs on the FP64 pipe.
-// A warp runs until its slowest gene has converged (finished lanes idle); genes can be handed out in the order of their
+// Mapping: ONE GENE PER THREAD, the whole solver state (q = X'y - X'X beta and beta, 2 x KT doubles) in registers. The
+// visiting order of a sweep depends only on (seed, ALS iteration, sweep index) - common.cuh:perm_key - so all 32 genes of a
+// warp start at sweep 0 together and visit the SAME coordinate at every step: the coordinate is warp-uniform. Per sweep
+// the warp
+//   * relabels q and beta into visiting order (thread-private transposition through shared memory), so that step i of the
+//     fully unrolled sweep touches registers q[i], b[i]: no dynamic register index, no dispatch, one basic block per sweep;
+//   * reads row i of a copy of XtX permuted into the same order (built for the NEXT sweep while this one runs).
+// What bounds it (ncu, profiles/r01_ncu_k_cd_dense_*.txt): every step needs the 24 doubles of the table row in every
+// thread, and a broadcast LDS costs one shared-memory wavefront per double: the shared-memory data pipe runs at 85 % of its
+// peak with the FP64 pipe at 35-38 %. Measured alternatives: XtX through the constant bank (ptxas emits LDCU.128 into two
+// uniform-register quads and serialises on them: 1.6x slower); two genes per thread sharing every row load (half the
+// wavefronts per gene, but half the warps at the same cycles-per-instruction: 1.15x slower); `switch (k)` on coordinate-
+// order registers instead of relabelling (same wavefronts, plus dispatch: 1.05x slower).
+// A warp runs until its slowest gene has converged (finished genes idle); genes can be handed out in the order of their
 // previous sweep counts (`order`) so that a warp's genes finish together. Arithmetic per coordinate (covariance form,
 // exact loss decrements, correctly rounded division) is identical to k_cd.cu - see the header comment there.
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -22,7 +29,7 @@ namespace ib {
 
 namespace {
 
-constexpr int DW = 4;                // warps per block
+constexpr int DW = 1;                // warps per block: one-warp blocks spread evenly over the SMs
 constexpr int MAX_SWEEPS_D = 200000;
 
 struct CdDenseArgs {
@@ -38,52 +45,84 @@ struct CdDenseArgs {
     uint64_t seed; int perm_mode;
     unsigned long long* sweeps_total; unsigned long long* steps_total;
     int* sweeps_per_gene;            // optional [P]
-    const int* order;                // optional [P]: thread i solves gene order[i]
+    const int* order;                // optional [P]: slot i solves gene order[i]
     const unsigned char* perm_table;
 };
 
-// volatile: the table is loop-invariant, and without it the compiler hoists all KT x (KT+4) loads out of the sweep loop
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-    return v;
-}
+// byte j of a packed byte array held in 32-bit words (compile-time j)
+template <int NW>
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[NW], int j) { return (w[j >> 2] >> (8 * (j & 3))) & 0xffu; }
 
-// one coordinate update of coordinate C (compile-time) for this thread's gene; row = shared-memory row C of the table
-//   row[0..KT)  XtX[C][:]     row[KT] XtX_CC     row[KT+1] XtX_CC + l2     row[KT+2] 1/(XtX_CC + l2)   row[KT+3] (XtX_CC + l2)/2
-template <int KT, int C>
-__device__ __forceinline__ void cd_step(double (&q)[KT], double (&b)[KT], uint32_t xbase, bool on, double la, double& dl) {
-    constexpr uint32_t row = (uint32_t)C * (KT + 4) * 8u;                     // compile-time shared-memory offset
-    const double2 dd = lds128(xbase + row + KT * 8u);                        // d, den
-    const double2 rr = lds128(xbase + row + (KT + 2) * 8u);                  // 1/den, den/2
-    const double bo = b[C];
-    const double up = fma(bo, dd.x, q[C]);                                   // coordinate_descent.cpp:94
+// One coordinate update at POSITION I of the sweep (compile-time) for this thread's gene. q and b are held in visiting
+// order (position layout), Xp is the warp's XtX table permuted into the same order:
+//   row[0..KT)  XtX[k_I][k_l]   row[KT] XtX_kk   row[KT+1] XtX_kk + l2   row[KT+2] 1/(XtX_kk + l2)   row[KT+3] (XtX_kk + l2)/2
+template <int KT, int I>
+__device__ __forceinline__ void cd_step(double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp, uint32_t incp, double la, double& dl) {
+    const double* row = Xp + I * (KT + 4);                                   // compile-time shared-memory offset, warp-uniform
+    const double2 dd = *reinterpret_cast<const double2*>(row + KT);          // d, den
+    const double2 rr = *reinterpret_cast<const double2*>(row + KT + 2);      // 1/den, den/2
+    const bool on = (incp >> I) & 1u;
+    const double bo = b[I];
+    const double up = fma(bo, dd.x, q[I]);                                   // coordinate_descent.cpp:94
     const double t1 = fabs(up) - la;
     const double num = copysign(t1, up);
     double nb = num * rr.x;                                                  // :99-104, correctly rounded num / den
     nb = fma(fma(-dd.y, nb, num), rr.x, nb);
-    nb = (t1 > 0.0) ? nb : 0.0;
+    nb = (__double2hiint(t1) >= 0) ? nb : 0.0;                               // t1 > 0 (t1 == +0 gives nb == 0 either way); integer test: one FP64-pipe op less
     nb = on ? nb : bo;                                                       // excluded coordinate / finished gene: no-op
     const double dlt = nb - bo;
-    // exact loss decrement of this update: dlt ((XtX_CC + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
+    // exact loss decrement of this update: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
     dl = fma(dlt, fma(rr.y, nb + bo, -up), dl);
     dl = fma(la, fabs(nb) - fabs(bo), dl);
-    b[C] = nb;                                                               // :106-109
+    b[I] = nb;                                                               // :106-109
     const double nd = -dlt;
 #pragma unroll
     for (int l = 0; l < KT; l += 2) {
-        const double2 x = lds128(xbase + row + l * 8u);
+        const double2 x = *reinterpret_cast<const double2*>(row + l);
         q[l] = fma(nd, x.x, q[l]);
         q[l + 1] = fma(nd, x.y, q[l + 1]);
     }
 }
 
-template <int KT>
-__global__ void __launch_bounds__(DW * 32) k_cd_dense(CdDenseArgs a) {
+// row I of a table in visiting order `ow` (order bytes): Xn[I][l] = XtX[k_I][k_l], per-row constants copied from row k_I.
+// Positions >= K are the identity and hit zero rows of Xs. Lane l writes column l (and l + 32 when the row is longer).
+template <int KT, int I>
+__device__ __forceinline__ void build_row(double* __restrict__ Xn, const double* __restrict__ Xs, const uint32_t (&ow)[KT / 4], int srcA, int lane) {
     constexpr int XLD = KT + 4;
-    __shared__ __align__(16) double Xs[KT * XLD];
-    __shared__ __align__(16) unsigned char ord_s[DW][2][32];
+    const double* srow = Xs + byte_of(ow, I) * XLD;
+    if (lane < XLD) Xn[I * XLD + lane] = srow[srcA];
+    if (XLD > 32 && lane + 32 < XLD) Xn[I * XLD + lane + 32] = srow[lane + 32];
+}
+template <int KT, int... Is>
+__device__ __forceinline__ void build_table(std::integer_sequence<int, Is...>, double* __restrict__ Xn, const double* __restrict__ Xs,
+                                            const uint32_t (&ow)[KT / 4], int srcA, int lane) {
+    (build_row<KT, Is>(Xn, Xs, ow, srcA, lane), ...);
+}
+// One sweep on table Xp, straight-line over all KT positions (the KT - K <= 3 padding positions are never active and their
+// table rows are zero: exact no-ops, and no branch keeps the sweep one basic block). The rows of the NEXT sweep's table are
+// built in between, off the critical path.
+template <int KT, int... Is>
+__device__ __forceinline__ void cd_sweep(std::integer_sequence<int, Is...>, double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp,
+                                         uint32_t incp, double la, double& dl, double* __restrict__ Xn, const double* __restrict__ Xs,
+                                         const uint32_t (&ow)[KT / 4], int srcA, int lane) {
+    ((cd_step<KT, Is>(q, b, Xp, incp, la, dl), build_row<KT, Is>(Xn, Xs, ow, srcA, lane)), ...);
+}
+
+template <int KT>
+// 8 one-warp blocks per SM = 255 registers: the lone-warp sweep takes 2.3 us against 3.6 us at 168 registers (ptxas keeps more
+// table rows in flight), which is what the tail of every launch and the small shards of a multi-GPU run see
+__global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
+    constexpr int XLD = KT + 4;
+    constexpr int NW = KT / 4;                         // 32-bit words holding KT position bytes
+    constexpr int WBUF = (KT * 32 > KT * XLD) ? KT * 32 : KT * XLD;          // one warp buffer: permuted table, then relabel scratch
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* Xs = reinterpret_cast<double*>(smem_raw);                        // block: XtX table in coordinate order
+    double* Xw = Xs + KT * XLD + warp * 2 * WBUF;                            // warp: two buffers (current / next sweep)
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(Xs + KT * XLD + DW * 2 * WBUF) + warp * 128;
+    unsigned char* ord_s = bytes;                                            // [2][32] visiting order of the current / next sweep
+    unsigned char* rank_s = bytes + 64;                                      // [32] rank of every coordinate in the next order
+    unsigned char* np_s = bytes + 96;                                        // [32] next position of the value at current position j
     const int K = a.K;
     const double la = a.la, l2 = a.l2;
     const double tol = a.tol_dev ? *a.tol_dev : a.tol_host;
@@ -99,17 +138,18 @@ __global__ void __launch_bounds__(DW * 32) k_cd_dense(CdDenseArgs a) {
                 const double d = a.XtX[(size_t)r * a.xs_r + (size_t)r * a.xs_c], den = d + l2;
                 v = (c == KT) ? d : (c == KT + 1) ? den : (c == KT + 2) ? 1.0 / den : 0.5 * den;
             }
-        } else if (c == KT + 2) v = 1.0;
+        }
         Xs[x] = v;
     }
+    ord_s[lane] = (unsigned char)lane;                                       // order before the first sweep: identity (positions = coordinates)
     __syncthreads();
 
-    // ---- this thread's gene
+    // ---- this thread's gene; positions = coordinates until the first sweep relabels them
     const int64_t slot = (int64_t)blockIdx.x * (DW * 32) + tid;
     bool active = slot < a.P;
     const int64_t gene = active ? (a.order ? (int64_t)a.order[slot] : slot) : 0;
     double q[KT], b[KT];
-    uint32_t inc = 0;
+    uint32_t incp = 0;                                                       // active set, indexed by POSITION
     {
         const double* xp = a.Xty + gene * a.ldv;
         const double* wp = a.W0 + gene * a.ldv;
@@ -125,7 +165,7 @@ __global__ void __launch_bounds__(DW * 32) k_cd_dense(CdDenseArgs a) {
         for (int c = 0; c < KT; ++c) {
             const bool on = active && (c < K) && !(fabs(q[c]) < thr);
             if (!on) b[c] = 0.0;                                             // :75-78
-            inc |= (on ? 1u : 0u) << c;
+            incp |= (on ? 1u : 0u) << c;
         }
         // q = X'y - X'X beta   (:79, in covariance form); coordinates in ascending order like k_cd.cu
 #pragma unroll
@@ -139,59 +179,97 @@ __global__ void __launch_bounds__(DW * 32) k_cd_dense(CdDenseArgs a) {
             }
         }
     }
+    const uint32_t full = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
     int sweeps = 0;
     unsigned long long steps_acc = 0;
-    const uint32_t xbase = smem_u32(Xs);
 
-    // visiting order of sweep `draw`: order-table row of K coordinates (identity when perm_mode != 1)
+    // table rows of sweep `dr`: lanes 0-7 fetch the 8 words of the order row (coordinate at every position), lanes 8-15 the
+    // rank row (position of every coordinate); identity when perm_mode != 1
     auto row_word = [&](uint32_t dr) -> uint32_t {
-        if (a.perm_mode != 1) { const uint32_t c0 = 4u * (lane & 7); return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24); }
+        const uint32_t c0 = 4u * (lane & 7);
+        if (a.perm_mode != 1) return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24);
         const uint64_t pk = key_iter ^ mix64((uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
-        return __ldg(reinterpret_cast<const uint32_t*>(a.perm_table + PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + (lane & 7));
+        const unsigned char* rowp = a.perm_table + ((lane & 8) ? 0 : PERM_TABLE_HALF) + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32;
+        return __ldg(reinterpret_cast<const uint32_t*>(rowp) + (lane & 7));
     };
-    uint32_t draw = 0;
-    uint32_t row_w = row_word(0);
-    int cur = 0;
-    while (true) {
-        if (lane < 8) reinterpret_cast<uint32_t*>(ord_s[warp][cur])[lane] = row_w;
-        __syncwarp();
-        row_w = row_word(draw + 1);                                          // prefetched, consumed by the next sweep
-        const unsigned char* ord = ord_s[warp][cur];
-        double dl = 0.0;
-        int k = ord[0];
-        for (int i = 0; i < K; ++i) {
-            const int kn = ord[(i + 1 < K) ? i + 1 : i];
-            const bool on = (inc >> k) & 1u;
-            switch (k) {
-#define CD_CASE(Cv) case Cv: if constexpr (Cv < KT) cd_step<KT, (Cv < KT ? Cv : 0)>(q, b, xbase, on, la, dl); break;
-                CD_CASE(0) CD_CASE(1) CD_CASE(2) CD_CASE(3) CD_CASE(4) CD_CASE(5) CD_CASE(6) CD_CASE(7)
-                CD_CASE(8) CD_CASE(9) CD_CASE(10) CD_CASE(11) CD_CASE(12) CD_CASE(13) CD_CASE(14) CD_CASE(15)
-                CD_CASE(16) CD_CASE(17) CD_CASE(18) CD_CASE(19) CD_CASE(20) CD_CASE(21) CD_CASE(22) CD_CASE(23)
-                CD_CASE(24) CD_CASE(25) CD_CASE(26) CD_CASE(27) CD_CASE(28) CD_CASE(29) CD_CASE(30) CD_CASE(31)
-#undef CD_CASE
-                default: break;
-            }
-            k = kn;
+    // relabels this gene's state into the next visiting order (np_s: next position of the value at current position j) through
+    // the thread-private column of `scratch` (a table buffer that is dead at that point)
+    auto relabel = [&](double* scratch) {
+        uint32_t npw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) npw[w] = reinterpret_cast<const uint32_t*>(np_s)[w];
+        double* col = scratch + lane;
+#pragma unroll
+        for (int j = 0; j < KT; ++j) col[byte_of(npw, j) * 32] = q[j];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) q[i] = col[i * 32];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) col[byte_of(npw, j) * 32] = b[j];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) b[i] = col[i * 32];
+        if (__any_sync(FULL, incp != full && incp != 0u)) {                  // screened coordinates: rare
+            uint32_t n = 0;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) n |= ((incp >> j) & 1u) << byte_of(npw, j);
+            incp = n;
         }
+    };
+    // publishes the fetched table rows as the order `into` (0/1) and np_s = positions in it of the values now ordered by `from`
+    auto publish_next = [&](uint32_t row_w, int into, int from) {
+        if (lane < 8) reinterpret_cast<uint32_t*>(ord_s + 32 * into)[lane] = row_w;
+        else if (lane < 16) reinterpret_cast<uint32_t*>(rank_s)[lane - 8] = row_w;
+        __syncwarp();
+        np_s[lane] = (lane < K) ? rank_s[ord_s[32 * from + lane]] : (unsigned char)lane;
+        __syncwarp();
+    };
+    // ---- prologue: order of sweep 0, state relabelled into it, its table built; order words of sweep 1 in flight
+    uint32_t draw = 0;
+    publish_next(row_word(0), 1, 0);
+    uint32_t row_w = row_word(1);
+    relabel(Xw);
+    __syncwarp();
+    int cur = 1;                                                             // ord_s[cur]: order of the sweep about to run; table in Xw + cur*WBUF
+    {
+        uint32_t ow[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s + 32 * cur)[w];
+        const int srcA = (lane < K) ? (int)ord_s[32 * cur + lane] : lane;
+        build_table<KT>(std::make_integer_sequence<int, KT>{}, Xw + cur * WBUF, Xs, ow, srcA, lane);
+    }
+    while (true) {
+        // order of the next sweep (prefetched words) and the relabelling into it; then its table is built during this sweep
+        publish_next(row_w, cur ^ 1, cur);                                   // (its __syncwarp also orders the table build / relabel of the last sweep)
+        row_w = row_word(draw + 2);                                          // consumed by the sweep after the next one
+        const double* Xp = Xw + cur * WBUF;
+        double* Xn = Xw + (cur ^ 1) * WBUF;
+        uint32_t ow[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s + 32 * (cur ^ 1))[w];
+        const int srcA = (lane < K) ? (int)ord_s[32 * (cur ^ 1) + lane] : lane;
+        double dl = 0.0;
+        cd_sweep<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, dl, Xn, Xs, ow, srcA, lane);
         // ---- end of the sweep for this gene: inner do-while test (:114), KKT re-admission (:118-124)
         if (active) {
             ++sweeps;
-            steps_acc += (unsigned long long)__popc(inc);
+            steps_acc += (unsigned long long)__popc(incp);
             if (!(fabs(dl) > tol) || sweeps >= MAX_SWEEPS_D) {
                 uint32_t vmask = 0;
 #pragma unroll
-                for (int c = 0; c < KT; ++c)
-                    if (c < K && !((inc >> c) & 1u) && fabs(q[c]) > la) vmask |= 1u << c;     // |XtX[e,inc] beta - Xty_e| = |q_e| (beta_e = 0)
+                for (int i = 0; i < KT; ++i)
+                    if (i < K && !((incp >> i) & 1u) && fabs(q[i]) > la) vmask |= 1u << i;    // |XtX[e,inc] beta - Xty_e| = |q_e| (beta_e = 0)
                 if (vmask == 0u || sweeps >= MAX_SWEEPS_D) {
                     double* vp = a.Vout + gene * a.ldv;
+                    const unsigned char* oc = ord_s + 32 * cur;
 #pragma unroll
-                    for (int c = 0; c < KT; ++c) if (c < K) vp[c] = b[c];
+                    for (int i = 0; i < KT; ++i) if (i < K) vp[oc[i]] = b[i];
                     if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps;
-                    active = false; inc = 0;
-                } else inc |= vmask;
+                    active = false; incp = 0;
+                } else incp |= vmask;
             }
         }
         if (!__any_sync(FULL, active)) break;
+        __syncwarp();                                                        // every lane is done reading this sweep's table
+        relabel(Xw + cur * WBUF);                                            // ... which now serves as the relabel scratch
         ++draw; cur ^= 1;
     }
     // one atomic per warp for the statistics
@@ -204,19 +282,100 @@ __global__ void __launch_bounds__(DW * 32) k_cd_dense(CdDenseArgs a) {
     }
 }
 
+// Slot order for the next launch: genes sorted by descending sweep count of the previous iteration (bucketed to ~3 %:
+// exponent + 5 mantissa bits), so that the 32 genes of a warp finish together and the longest warps start first.
+// Consecutive iterations correlate at 0.95+ (tools/gpu_sweep_dist.py): lockstep efficiency 0.58 -> 0.85. The order within a
+// bucket depends on atomics; results do not depend on the order at all (every gene is solved independently).
+constexpr int ORDER_BUCKETS = 32 * 19;
+__device__ __forceinline__ int order_key(int s) {
+    const uint32_t v = (uint32_t)max(s, 0) + 1u;
+    const int e = 31 - __clz(v);
+    const uint32_t m = ((v << (31 - e)) >> 26) & 31u;
+    return ORDER_BUCKETS - 1 - min(ORDER_BUCKETS - 1, e * 32 + (int)m);     // descending
+}
+constexpr int ORDER_BLOCKS = 32, ORDER_THREADS = 256;
+// adds 1 to counter[key] for every lane of the warp, one atomic per distinct key (sweep counts cluster on a few buckets);
+// returns the value this lane's increment would have received. key < 0: lane does not take part.
+__device__ __forceinline__ int warp_agg_inc(int* counter, int key) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __match_any_sync(FULL, key);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)lane == leader && key >= 0) base = atomicAdd(&counter[key], __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+// work: [ORDER_BUCKETS] bucket totals | arrive counter | done counter  (all zero between launches)
+__global__ void __launch_bounds__(ORDER_THREADS) k_cd_order(const int* __restrict__ sweeps, int P, int* __restrict__ order, int* __restrict__ work,
+                                                            const uint32_t* __restrict__ als_iter) {
+    // sweep counts of consecutive iterations correlate at 0.95+: after the first iterations a new order every 8th is enough
+    if (als_iter) { const uint32_t it = *als_iter; if (it >= 8u && (it & 7u) != 0u) return; }
+    __shared__ int hist[ORDER_BUCKETS];      // this block's count per bucket, later its scatter cursor
+    __shared__ int boff[ORDER_BUCKETS];      // start of this block's genes inside the bucket, later + start of the bucket
+    __shared__ int last;
+    int* gtot = work; int* arrive = work + ORDER_BUCKETS; int* done = arrive + 1;
+    const int tid = threadIdx.x, gtid = blockIdx.x * ORDER_THREADS + tid, gsz = gridDim.x * ORDER_THREADS;
+    const int Pw = (P + 31) / 32 * 32;
+    for (int x = tid; x < ORDER_BUCKETS; x += ORDER_THREADS) hist[x] = 0;
+    __syncthreads();
+    for (int j = gtid; j < Pw; j += gsz) warp_agg_inc(hist, j < P ? order_key(sweeps[j]) : -1);
+    __syncthreads();
+    for (int x = tid; x < ORDER_BUCKETS; x += ORDER_THREADS) { boff[x] = hist[x] ? atomicAdd(&gtot[x], hist[x]) : 0; hist[x] = 0; }
+    // grid barrier (all ORDER_BLOCKS blocks are co-resident: far fewer than SMs)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { atomicAdd(arrive, 1); while (atomicAdd(arrive, 0) < (int)gridDim.x) { } }
+    __syncthreads();
+    if (tid < 32) {                                                          // exclusive scan of the totals, one warp, 19 buckets per lane
+        constexpr int PER = ORDER_BUCKETS / 32;
+        int loc[PER], sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { loc[u] = sum; sum += __ldcg(&gtot[tid * PER + u]); }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (tid >= o) incl += v; }
+        const int base = incl - sum;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) boff[tid * PER + u] += base + loc[u];
+    }
+    __syncthreads();
+    for (int j = gtid; j < Pw; j += gsz) {
+        const int k = j < P ? order_key(sweeps[j]) : -1;
+        const int r = warp_agg_inc(hist, k);
+        if (k >= 0) order[boff[k] + r] = j;
+    }
+    // the last block to finish zeroes the work area for the next launch
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        for (int x = tid; x < ORDER_BUCKETS + 2; x += ORDER_THREADS) work[x] = 0;
+    }
+}
+
+template <int KT>
+void launch_kt(const CdDenseArgs& a, cudaStream_t st) {
+    constexpr int XLD = KT + 4;
+    constexpr int WBUF = (KT * 32 > KT * XLD) ? KT * 32 : KT * XLD;
+    const int blocks = (int)((a.P + DW * 32 - 1) / (DW * 32));
+    const size_t smem = (size_t)(KT * XLD + DW * 2 * WBUF) * 8 + DW * 128;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_cd_dense<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cd_dense<KT><<<blocks, DW * 32, smem, st>>>(a);
+}
+
 void launch(CdDenseArgs a, cudaStream_t st) {
     a.la = a.lambda * a.alpha; a.l2 = a.lambda * (1.0 - a.alpha);
-    const int blocks = (int)((a.P + DW * 32 - 1) / (DW * 32));
-    if (blocks == 0) return;
+    if (a.P <= 0) return;
     switch ((a.K + 3) / 4) {
-        case 1: k_cd_dense<4><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 2: k_cd_dense<8><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 3: k_cd_dense<12><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 4: k_cd_dense<16><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 5: k_cd_dense<20><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 6: k_cd_dense<24><<<blocks, DW * 32, 0, st>>>(a); break;
-        case 7: k_cd_dense<28><<<blocks, DW * 32, 0, st>>>(a); break;
-        default: k_cd_dense<32><<<blocks, DW * 32, 0, st>>>(a); break;
+        case 1: launch_kt<4>(a, st); break;
+        case 2: launch_kt<8>(a, st); break;
+        case 3: launch_kt<12>(a, st); break;
+        case 4: launch_kt<16>(a, st); break;
+        case 5: launch_kt<20>(a, st); break;
+        case 6: launch_kt<24>(a, st); break;
+        case 7: launch_kt<28>(a, st); break;
+        default: launch_kt<32>(a, st); break;
     }
 }
 
@@ -230,6 +389,11 @@ void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
     a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.perm_table = perm_table;
     launch(a, st);
+}
+
+size_t cd_order_work_ints() { return ORDER_BUCKETS + 2; }
+void launch_cd_order(const int* sweeps_per_gene, int64_t P, int* order, int* work, const uint32_t* als_iter, cudaStream_t st) {
+    if (P > 0) k_cd_order<<<ORDER_BLOCKS, ORDER_THREADS, 0, st>>>(sweeps_per_gene, (int)P, order, work, als_iter);
 }
 
 void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xty, const double* w0, double lambda, double alpha, double tol,

@@ -137,6 +137,9 @@ struct insider_session {
     CheckState* state = nullptr;
     insider_check* records_dev = nullptr;
     unsigned long long* sweeps_dev = nullptr;
+    int* sweeps_gene = nullptr;          // dense CD: sweeps of every local gene in the last iteration
+    int* cd_order = nullptr;             // dense CD: slot -> gene, sorted by the last iteration's sweep counts
+    int* cd_order_work = nullptr;
     int* err_dev = nullptr;
     uint32_t max_records = 0, n_records = 0;
     uint32_t iter = 0;
@@ -458,8 +461,9 @@ void run_iteration(insider_session* s) {
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
     if (!s->masked && s->opt.alpha != 0.0) {
+        { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
         Launch l(s, "k_cd_dense");
-        launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, nullptr, nullptr, s->ctx->perm_table, st);
+        launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, st);
     } else {
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
@@ -553,6 +557,9 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->records_dev = s->pool.get<insider_check>(s->max_records, true, st);
         s->sweeps_dev = s->pool.get<unsigned long long>(2, true, st);   // [sweeps, coordinate steps]
         s->queue = s->pool.get<unsigned int>(1, true, st);
+        s->sweeps_gene = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
+        s->cd_order = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
+        s->cd_order_work = s->pool.get<int>(cd_order_work_ints(), true, st);
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
         upload_factors(s, f);
@@ -767,6 +774,15 @@ int insider_b200_als_profile(insider_session* s, char* names, size_t names_len, 
         ++n;
     }
     if (names && names_len) { strncpy(names, joined.c_str(), names_len - 1); names[names_len - 1] = 0; }
+    return n;
+}
+
+int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n) {
+    if (!s || !out || n <= 0 || s->masked || s->opt.alpha == 0.0) return 0;
+    n = std::min<int64_t>(n, s->g.P);
+    if (cudaSetDevice(s->ctx->device) != cudaSuccess) return 0;
+    if (cudaMemcpyAsync(out, s->sweeps_gene, (size_t)n * 4, cudaMemcpyDeviceToHost, s->ctx->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(s->ctx->stream) != cudaSuccess) return 0;
     return n;
 }
 

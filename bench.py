@@ -232,23 +232,32 @@ def run_ours(args, w, rank, world, local):
         # q -= delta * XtX[:,k] update + 12 for the soft-threshold / exact division / loss-decrement chain.
         FP64_PEAK = 37.1   # TFLOP/s, measured on this pool by tools/microbench.cu (profiles/r01_microbench_fp64_hbm.txt)
         cd = None
-        if "k_col_solve" in kern:
+        cd_name = "k_cd_dense" if "k_cd_dense" in kern else ("k_col_solve" if "k_col_solve" in kern else None)
+        if cd_name:
             steps_cd, sweeps = outp["cd_steps"], outp["cd_sweeps"]
-            secs = kern["k_col_solve"]["ms_total"] * 1e-3
+            secs = kern[cd_name]["ms_total"] * 1e-3
             flops = steps_cd * (2.0 * K + 12.0)
-            cd = {"gene_sweeps": sweeps, "coordinate_updates": steps_cd, "gene_sweeps_per_s": sweeps / secs,
+            cd = {"kernel": cd_name, "gene_sweeps": sweeps, "coordinate_updates": steps_cd, "gene_sweeps_per_s": sweeps / secs,
                   "algorithmic_flops": flops, "fp64_tflops": flops / secs / 1e12, "fp64_peak_tflops_measured": FP64_PEAK,
-                  "share_of_iteration": kern["k_col_solve"]["share"]}
+                  "share_of_iteration": kern[cd_name]["share"]}
         roof_dom = None
         if cd:
-            roof_dom = {"bound": "tensor", "kernel": "k_cd_persistent (launched as k_col_solve)", "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
-                        "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": None,
+            note = ("thread-per-gene coordinate descent, K=23: every step needs the 24-double table row in every thread; ncu shows the "
+                    "shared-memory data pipe at 93 % of peak (l1tex__throughput) with the FP64 pipe at 38 %; lockstep warps run until their "
+                    "slowest gene converges (lane efficiency 0.47-0.85). See profiles/r01_ncu_k_cd_dense_v4_dense_A.txt"
+                    if cd_name == "k_cd_dense" else
+                    "8-lanes-per-gene coordinate descent with per-gene Gram matrices: bound by the shared-memory pipe; "
+                    "see profiles/r01_ncu_k_cd_persistent_*.txt")
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture of this command's shape
+            # (profiles/r01_ncu_k_cd_dense_v4_dense_A.txt: 20.39 MB read, 0 written; algorithmic Xty + V = 18.6 MB)
+            traffic = 20393216 if (cd_name == "k_cd_dense" and world == 1 and args.workload == "ageing_full_377x44477_K23_fit") else None
+            roof_dom = {"bound": "tensor", "kernel": cd_name, "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
+                        "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": traffic,
                         "peak_source": "FP64 pipe peak measured with DMMA m8n8k4 by tools/microbench.cu on this pool's B200 (MEASURED_PEAKS.json has "
                                        "no FP64 entry; its bf16 tensor peak does not apply to an FP64 path)",
-                        "note": "sequential coordinate descent on K=23 vectors: bound by instruction issue / FP64 latency chains, not by a "
-                                "throughput roof; issue-slot utilisation and stall reasons are in profiles/r01_ncu_k_cd_persistent_*.txt",
-                        "algorithmic_flops_per_launch": flops / max(1, kern["k_col_solve"]["calls"]),
-                        "avg_launch_ms": kern["k_col_solve"]["ms_total"] / max(1, kern["k_col_solve"]["calls"])}
+                        "note": note,
+                        "algorithmic_flops_per_launch": flops / max(1, kern[cd_name]["calls"]),
+                        "avg_launch_ms": kern[cd_name]["ms_total"] / max(1, kern[cd_name]["calls"])}
         roof_iter = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_iteration": b_iter,
                      "what": "whole ALS iteration, SURVEY.md 8(d) bytes / mean iteration time (per GPU)", "dominant_kernel": dominant}

@@ -206,6 +206,59 @@ def test_batched_strong_cd_entry(ctx):
         assert np.all(np.abs(grad[~on]) <= la + 2e-2)
 
 
+def test_strong_cd_screening_and_kkt_readmission_paths(ctx):
+    """coordinate_descent.cpp:74-78 (strong-rule screen) and :118-124 (KKT re-admission) in both GPU solvers: problems whose
+    active set starts partial and grows (oracle rounds > 1), every K the kernels are instantiated for."""
+    rng = np.random.default_rng(11)
+    hit = 0
+    for K in (3, 5, 9, 14, 18, 23, 27, 30):
+        n, n_cols = 60, 48
+        X = rng.normal(size=(n, K)) @ (np.eye(K) + 0.6 * rng.normal(size=(K, K)) / np.sqrt(K))
+        G = X.T @ X
+        B = rng.normal(size=(K, n_cols)) * (rng.random((K, n_cols)) < 0.3)
+        Y = 0.25 * (X @ B) + 0.05 * rng.normal(size=(n, n_cols))
+        Xty = X.T @ Y
+        w0 = 0.05 * rng.normal(size=(K, n_cols))
+        lam = float(0.55 * np.abs(Xty).max())                   # 2*lam - max|Xty_j| > 0 for every column: the screen bites
+        alpha = 0.7
+        beta, sweeps = ctx.strong_cd(G, Xty, w0, lam, alpha, tol=1e-9, seed=3, als_iter=1)
+        Gs = np.stack([G] * n_cols)
+        beta2, sweeps2 = ctx.strong_cd(Gs, Xty, w0, lam, alpha, tol=1e-9, seed=3, als_iter=1)
+        for j in range(n_cols):
+            bo, sw, rounds = oracle.strong_cd(X, Y[:, j], w0[:, j], lam, alpha, G, Xty[:, j], tol=1e-9, perm_mode=1, seed=3, als_iter=1, gene=j)
+            hit += rounds > 1
+            for b, s_ in ((beta, sweeps), (beta2, sweeps2)):
+                assert np.abs(b[:, j] - bo).max() <= 1e-10 * max(1.0, np.abs(bo).max())
+                assert s_[j] == sw
+    assert hit >= 10                                             # the re-admission path really ran
+
+
+def test_per_gene_sweep_counts_match_oracle(ctx):
+    """insider_b200_als_sweeps: the do-while count of every gene in the last iteration equals the oracle's, gene by gene
+    (and does not depend on the slot order the dense solver derives from the previous iteration's counts)."""
+    import ctypes as C
+    N, P, K = 40, 300, 6
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=7, seed=4)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=5)
+    iters = 4
+    sink = np.zeros((iters + 2, P), dtype=np.int32)
+    oracle.lib().oracle_set_sweep_sink(sink.ctypes.data_as(C.POINTER(C.c_int)), C.c_longlong(sink.size))
+    try:
+        oracle.optimize(pb.Y, F0, V0, pb.confounder, None, None, None, 0, K, 3.0, 3.0, 0.4, 0, 1e-12, 1e-5, iters - 1, perm_mode=1, seed=9)
+    finally:
+        oracle.lib().oracle_set_sweep_sink(None, C.c_longlong(0))
+    res = ctx.upload(_cabi.HostProblem(pb.Y, pb.confounder, None, None, None, 0))
+    opt = _cabi.default_options()
+    opt.lambda1 = opt.lambda2 = 3.0
+    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = 0.4, 0, 1e-12, 1e-5, 10 ** 6, 9
+    s = res.begin(_cabi.HostFactors(F0, V0, K), opt)
+    for it in range(iters):
+        s.step(1)
+        np.testing.assert_array_equal(s.sweeps(P), sink[it])
+    s.end(read_factors=False)
+    res.release()
+
+
 def test_fit_interaction_entry(ctx):
     rng = np.random.default_rng(8)
     N, P, K, L = 60, 130, 5, 7

@@ -120,6 +120,8 @@ void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const dou
 void launch_pack_mask(const void* src, int kind, int64_t N, int64_t n_genes, int Wp, uint32_t* dstC, cudaStream_t st);
 void launch_transpose_mask(const uint32_t* trC, int64_t N, int64_t P_pad, int Wp, int WPr, uint32_t* trR, cudaStream_t st);
 void launch_count_bits(const uint32_t* m, int64_t n_words, unsigned long long* out, cudaStream_t st);
+// dst[r*dst_ld + c] = src[r*src_ld + c], c < width (device re-pitch behind the contiguous host <-> device copies)
+void launch_repitch(double* dst, int64_t dst_ld, const double* src, int64_t src_ld, int width, int64_t rows, cudaStream_t st);
 struct CheckState {           // device-resident loop state
     double loss, pre_loss, decay, tol, sub_tol, global_tol;
     double sse_train, sse_test, v2, v1, row_reg;

@@ -218,9 +218,19 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
         // Y: column block [j0, j0+Pl) into pitch ldY, zero padded (+ slack for tile overhang reads)
         const size_t y_elems = (size_t)r->Pl_pad * r->ldY + 64;
         r->Y = r->pool.get<double>(y_elems, true, st);
-        if (r->Pl > 0)
-            CUDA_TRY(cudaMemcpy2DAsync(r->Y, (size_t)r->ldY * 8, pb->Y + (size_t)r->j0 * N, (size_t)N * 8, (size_t)N * 8, (size_t)r->Pl,
-                                       cudaMemcpyHostToDevice, st));
+        if (r->Pl > 0) {
+            // contiguous H2D into a staging buffer in column chunks, re-pitched on the device
+            const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(r->Pl, (int64_t)((size_t)256 << 20) / ((size_t)N * 8)));
+            double* stage = nullptr;
+            CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)chunk * N * 8, st));
+            for (int64_t c0 = 0; c0 < r->Pl; c0 += chunk) {
+                const int64_t n = std::min(chunk, r->Pl - c0);
+                cudaError_t e = cudaMemcpyAsync(stage, pb->Y + (size_t)(r->j0 + c0) * N, (size_t)n * N * 8, cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) { cudaFreeAsync(stage, st); CUDA_TRY(e); }
+                launch_repitch(r->Y + (size_t)c0 * r->ldY, r->ldY, stage, N, N, n, st);
+            }
+            cudaFreeAsync(stage, st);
+        }
         r->h2d_bytes += (double)r->Pl * N * 8;
         // design
         for (int c = 0; c < r->C; ++c) {
@@ -339,9 +349,10 @@ void upload_factors(insider_session* s, const insider_factors* f) {
     }
     CUDA_TRY(cudaMemcpyAsync(s->A_all, tmp.data(), s->n_A * 8, cudaMemcpyHostToDevice, s->ctx->stream));
     const insider_resident* r = s->r;
-    if (r->Pl > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(s->V, (size_t)s->g.ldV * 8, f->column_factor + (size_t)r->j0 * K, (size_t)K * 8, (size_t)K * 8, (size_t)r->Pl,
-                                   cudaMemcpyHostToDevice, s->ctx->stream));
+    if (r->Pl > 0) {                       // contiguous copy into the (not yet used) Xty buffer, re-pitched on the device
+        CUDA_TRY(cudaMemcpyAsync(s->Xty, f->column_factor + (size_t)r->j0 * K, (size_t)r->Pl * K * 8, cudaMemcpyHostToDevice, s->ctx->stream));
+        launch_repitch(s->V, s->g.ldV, s->Xty, K, K, r->Pl, s->ctx->stream);
+    }
     CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
     s->h2d += (double)s->n_A * 8 + (double)r->Pl * K * 8;
 }
@@ -353,7 +364,9 @@ void download_factors(insider_session* s, const insider_factors* f) {
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->A_all, s->n_A * 8, cudaMemcpyDeviceToHost, st));
     const insider_resident* r = s->r;
     if (s->ctx->world == 1) {
-        CUDA_TRY(cudaMemcpy2DAsync(f->column_factor, (size_t)K * 8, s->V, (size_t)s->g.ldV * 8, (size_t)K * 8, (size_t)r->Pl, cudaMemcpyDeviceToHost, st));
+        // pack V (pitch ldV) into the Xty buffer (free between iterations: k_col_xty rewrites it) and download it contiguously
+        launch_repitch(s->Xty, K, s->V, s->g.ldV, K, r->Pl, st);
+        CUDA_TRY(cudaMemcpyAsync(f->column_factor, s->Xty, (size_t)r->Pl * K * 8, cudaMemcpyDeviceToHost, st));
     } else {
         // gather every rank's gene block with one broadcast per rank, then one download of the full K x P matrix
         for (int rk = 0; rk < s->ctx->world; ++rk) {

@@ -55,24 +55,26 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[NW], int j) { re
 
 // One coordinate update at POSITION I of the sweep (compile-time) for this thread's gene. q and b are held in visiting
 // order (position layout), Xp is the warp's XtX table permuted into the same order:
-//   row[0..KT)  XtX[k_I][k_l]   row[KT] XtX_kk   row[KT+1] XtX_kk + l2   row[KT+2] 1/(XtX_kk + l2)   row[KT+3] (XtX_kk + l2)/2
+//   row[0..KT)  XtX[k_I][k_l]   row[KT] XtX_kk   row[KT+1] 1/(XtX_kk + l2)   (row pitch KT + 4 keeps 16-byte alignment)
 template <int KT, int I>
-__device__ __forceinline__ void cd_step(double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp, uint32_t incp, double la, double& dl) {
+__device__ __forceinline__ void cd_step(double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp, uint32_t incp, double la, double l2, double& dl) {
     const double* row = Xp + I * (KT + 4);                                   // compile-time shared-memory offset, warp-uniform
-    const double2 dd = *reinterpret_cast<const double2*>(row + KT);          // d, den
-    const double2 rr = *reinterpret_cast<const double2*>(row + KT + 2);      // 1/den, den/2
+    // one broadcast load for the row constants (a broadcast LDS costs a wavefront per double and the kernel is bound by them):
+    // d and 1/(d + l2) come from the table, d + l2 and (d + l2)/2 are recomputed (same roundings as the table's)
+    const double2 dr = *reinterpret_cast<const double2*>(row + KT);          // d, 1/den
+    const double den = dr.x + l2, hden = 0.5 * den;
     const bool on = (incp >> I) & 1u;
     const double bo = b[I];
-    const double up = fma(bo, dd.x, q[I]);                                   // coordinate_descent.cpp:94
+    const double up = fma(bo, dr.x, q[I]);                                   // coordinate_descent.cpp:94
     const double t1 = fabs(up) - la;
     const double num = copysign(t1, up);
-    double nb = num * rr.x;                                                  // :99-104, correctly rounded num / den
-    nb = fma(fma(-dd.y, nb, num), rr.x, nb);
+    double nb = num * dr.y;                                                  // :99-104, correctly rounded num / den
+    nb = fma(fma(-den, nb, num), dr.y, nb);
     nb = (__double2hiint(t1) >= 0) ? nb : 0.0;                               // t1 > 0 (t1 == +0 gives nb == 0 either way); integer test: one FP64-pipe op less
     nb = on ? nb : bo;                                                       // excluded coordinate / finished gene: no-op
     const double dlt = nb - bo;
     // exact loss decrement of this update: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
-    dl = fma(dlt, fma(rr.y, nb + bo, -up), dl);
+    dl = fma(dlt, fma(hden, nb + bo, -up), dl);
     dl = fma(la, fabs(nb) - fabs(bo), dl);
     b[I] = nb;                                                               // :106-109
     const double nd = -dlt;
@@ -103,9 +105,9 @@ __device__ __forceinline__ void build_table(std::integer_sequence<int, Is...>, d
 // built in between, off the critical path.
 template <int KT, int... Is>
 __device__ __forceinline__ void cd_sweep(std::integer_sequence<int, Is...>, double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp,
-                                         uint32_t incp, double la, double& dl, double* __restrict__ Xn, const double* __restrict__ Xs,
+                                         uint32_t incp, double la, double l2, double& dl, double* __restrict__ Xn, const double* __restrict__ Xs,
                                          const uint32_t (&ow)[KT / 4], int srcA, int lane) {
-    ((cd_step<KT, Is>(q, b, Xp, incp, la, dl), build_row<KT, Is>(Xn, Xs, ow, srcA, lane)), ...);
+    ((cd_step<KT, Is>(q, b, Xp, incp, la, l2, dl), build_row<KT, Is>(Xn, Xs, ow, srcA, lane)), ...);
 }
 
 template <int KT>
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
             if (c < KT) v = (c < K) ? a.XtX[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;
             else {
                 const double d = a.XtX[(size_t)r * a.xs_r + (size_t)r * a.xs_c], den = d + l2;
-                v = (c == KT) ? d : (c == KT + 1) ? den : (c == KT + 2) ? 1.0 / den : 0.5 * den;
+                v = (c == KT) ? d : (c == KT + 1) ? 1.0 / den : 0.0;
             }
         }
         Xs[x] = v;
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
         for (int w = 0; w < NW; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s + 32 * (cur ^ 1))[w];
         const int srcA = (lane < K) ? (int)ord_s[32 * (cur ^ 1) + lane] : lane;
         double dl = 0.0;
-        cd_sweep<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, dl, Xn, Xs, ow, srcA, lane);
+        cd_sweep<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, l2, dl, Xn, Xs, ow, srcA, lane);
         // ---- end of the sweep for this gene: inner do-while test (:114), KKT re-admission (:118-124)
         if (active) {
             ++sweeps;

@@ -35,6 +35,7 @@ constexpr int MAX_SWEEPS_D = 200000;
 struct CdDenseArgs {
     const double* XtX;               // K x K, element (r, c) at r*xs_r + c*xs_c
     int xs_r, xs_c;
+    const double* table;             // [KT][KT + 4] prepared by k_cd_table (row r: XtX[r][:], XtX_rr, 1/(XtX_rr + l2), 0, 0)
     const double* Xty; const double* W0; double* Vout;     // per gene, stride ldv (Vout may alias W0)
     int64_t ldv;
     int K; int64_t P;
@@ -110,10 +111,30 @@ __device__ __forceinline__ void cd_sweep(std::integer_sequence<int, Is...>, doub
     ((cd_step<KT, Is>(q, b, Xp, incp, la, l2, dl), build_row<KT, Is>(Xn, Xs, ow, srcA, lane)), ...);
 }
 
+// The XtX table in coordinate order, ready to be copied into shared memory by every block: row r = XtX[r][0..KT) (zero padded),
+// XtX_rr, 1/(XtX_rr + l2), 0, 0. One small launch per column update instead of 21 dependent global loads per thread in each of
+// the 1390 one-warp blocks.
+__global__ void __launch_bounds__(256) k_cd_table(const double* __restrict__ XtX, int xs_r, int xs_c, int K, int KT, double l2, double* __restrict__ out) {
+    const int XLD = KT + 4;
+    for (int x = threadIdx.x; x < KT * XLD; x += blockDim.x) {
+        const int r = x / XLD, c = x % XLD;
+        double v = 0.0;
+        if (r < K) {
+            if (c < KT) v = (c < K) ? XtX[(size_t)r * xs_r + (size_t)c * xs_c] : 0.0;
+            else if (c == KT) v = XtX[(size_t)r * xs_r + (size_t)r * xs_c];
+            else if (c == KT + 1) v = 1.0 / (XtX[(size_t)r * xs_r + (size_t)r * xs_c] + l2);
+        }
+        out[x] = v;
+    }
+}
+
+// MINB one-warp blocks per SM. MINB = 8 (255 registers): the lone-warp sweep takes 2.3 us against 2.8 us at 200 and 3.6 us at
+// 168 registers (ptxas keeps more table rows in flight) - the regime of the long early iterations, whose launches end with
+// the latency of their longest genes, and of the small shards of a multi-GPU run. MINB = 10 (200 registers): all 1390 blocks
+// of the 44 477-gene problem are resident at once; at steady state (4 sweeps per gene) a second wave of blocks costs more
+// than the slower sweep. lib.cu switches after the first iterations.
 template <int KT>
-// 8 one-warp blocks per SM = 255 registers: the lone-warp sweep takes 2.3 us against 3.6 us at 168 registers (ptxas keeps more
-// table rows in flight), which is what the tail of every launch and the small shards of a multi-GPU run see
-__global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
+__device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
     constexpr int XLD = KT + 4;
     constexpr int NW = KT / 4;                         // 32-bit words holding KT position bytes
     constexpr int WBUF = (KT * 32 > KT * XLD) ? KT * 32 : KT * XLD;          // one warp buffer: permuted table, then relabel scratch
@@ -131,17 +152,18 @@ __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
     const uint32_t als_iter = a.als_iter_dev ? *a.als_iter_dev : a.als_iter_host;
     const uint64_t key_iter = mix64(a.seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter));   // perm_key(): first factor
 
-    for (int x = tid; x < KT * XLD; x += DW * 32) {
-        const int r = x / XLD, c = x % XLD;
-        double v = 0.0;
-        if (r < K) {
-            if (c < KT) v = (c < K) ? a.XtX[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;
-            else {
-                const double d = a.XtX[(size_t)r * a.xs_r + (size_t)r * a.xs_c], den = d + l2;
-                v = (c == KT) ? d : (c == KT + 1) ? 1.0 / den : 0.0;
-            }
+    {   // prepared table -> shared memory, 16 bytes per load, all loads of a thread independent
+        const double2* src = reinterpret_cast<const double2*>(a.table);
+        double2* dst = reinterpret_cast<double2*>(Xs);
+        constexpr int N2 = KT * XLD / 2;
+#pragma unroll
+        for (int x0 = 0; x0 < N2; x0 += DW * 32 * 4) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int x = x0 + u * DW * 32 + tid; if (x < N2) v[u] = __ldg(src + x); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int x = x0 + u * DW * 32 + tid; if (x < N2) dst[x] = v[u]; }
         }
-        Xs[x] = v;
     }
     ord_s[lane] = (unsigned char)lane;                                       // order before the first sweep: identity (positions = coordinates)
     __syncthreads();
@@ -284,6 +306,10 @@ __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) {
     }
 }
 
+template <int KT> __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) { cd_dense_body<KT>(a); }
+// (__launch_bounds__(32, 10) makes ptxas stop at 168 registers; __maxnreg__ lets it use the 200 that 10 blocks per SM allow)
+template <int KT> __global__ void __maxnreg__(200) k_cd_dense_r200(CdDenseArgs a) { cd_dense_body<KT>(a); }
+
 // Slot order for the next launch: genes sorted by descending sweep count of the previous iteration (bucketed to ~3 %:
 // exponent + 5 mantissa bits), so that the 32 genes of a warp finish together and the longest warps start first.
 // Consecutive iterations correlate at 0.95+ (tools/gpu_sweep_dist.py): lockstep efficiency 0.58 -> 0.85. The order within a
@@ -356,41 +382,51 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_cd_order(const int* __restric
     }
 }
 
-template <int KT>
+template <int KT, int MINB>
 void launch_kt(const CdDenseArgs& a, cudaStream_t st) {
     constexpr int XLD = KT + 4;
     constexpr int WBUF = (KT * 32 > KT * XLD) ? KT * 32 : KT * XLD;
     const int blocks = (int)((a.P + DW * 32 - 1) / (DW * 32));
     const size_t smem = (size_t)(KT * XLD + DW * 2 * WBUF) * 8 + DW * 128;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_cd_dense<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_cd_dense<KT><<<blocks, DW * 32, smem, st>>>(a);
+    auto kern = (MINB == 8) ? k_cd_dense<KT> : k_cd_dense_r200<KT>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, DW * 32, smem, st>>>(a);
 }
 
-void launch(CdDenseArgs a, cudaStream_t st) {
+// `table`: device buffer of cd_dense_table_elems() doubles (filled here); resident_all: prefer the variant whose blocks all fit at once
+void launch(CdDenseArgs a, double* table, bool resident_all, cudaStream_t st) {
     a.la = a.lambda * a.alpha; a.l2 = a.lambda * (1.0 - a.alpha);
     if (a.P <= 0) return;
-    switch ((a.K + 3) / 4) {
-        case 1: launch_kt<4>(a, st); break;
-        case 2: launch_kt<8>(a, st); break;
-        case 3: launch_kt<12>(a, st); break;
-        case 4: launch_kt<16>(a, st); break;
-        case 5: launch_kt<20>(a, st); break;
-        case 6: launch_kt<24>(a, st); break;
-        case 7: launch_kt<28>(a, st); break;
-        default: launch_kt<32>(a, st); break;
+    const int KT = (a.K + 3) / 4 * 4;
+    k_cd_table<<<1, 256, 0, st>>>(a.XtX, a.xs_r, a.xs_c, a.K, KT, a.l2, table);
+    a.table = table;
+#define LAUNCH_KT(KTv) if (resident_all) launch_kt<KTv, 10>(a, st); else launch_kt<KTv, 8>(a, st); break;
+    switch (KT / 4) {
+        case 1: LAUNCH_KT(4)
+        case 2: LAUNCH_KT(8)
+        case 3: LAUNCH_KT(12)
+        case 4: LAUNCH_KT(16)
+        case 5: LAUNCH_KT(20)
+        case 6: LAUNCH_KT(24)
+        case 7: LAUNCH_KT(28)
+        default: LAUNCH_KT(32)
     }
+#undef LAUNCH_KT
 }
 
 }  // namespace
 
+size_t cd_dense_table_elems() { return (size_t)32 * 36; }
+
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
-                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, cudaStream_t st) {
+                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, double* table,
+                     bool resident_all, cudaStream_t st) {
     CdDenseArgs a{};
     a.XtX = UtU; a.xs_r = g.KP; a.xs_c = 1;
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
     a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.perm_table = perm_table;
-    launch(a, st);
+    launch(a, table, resident_all, st);
 }
 
 size_t cd_order_work_ints() { return ORDER_BUCKETS + 2; }
@@ -400,13 +436,13 @@ void launch_cd_order(const int* sweeps_per_gene, int64_t P, int* order, int* wor
 
 void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xty, const double* w0, double lambda, double alpha, double tol,
                            int perm_mode, uint64_t seed, uint32_t als_iter, double* beta, int* sweeps, const unsigned char* perm_table,
-                           cudaStream_t st) {
+                           double* table, cudaStream_t st) {
     CdDenseArgs a{};
     a.XtX = XtX; a.xs_r = 1; a.xs_c = K;                                     // caller's column-major K x K
     a.Xty = Xty; a.W0 = w0; a.Vout = beta; a.ldv = K; a.K = K; a.P = n;
     a.lambda = lambda; a.alpha = alpha; a.tol_dev = nullptr; a.tol_host = tol; a.als_iter_dev = nullptr; a.als_iter_host = als_iter;
     a.seed = seed; a.perm_mode = perm_mode; a.sweeps_per_gene = sweeps; a.perm_table = perm_table;
-    launch(a, st);
+    launch(a, table, false, st);
 }
 
 }  // namespace ib

@@ -101,15 +101,19 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
                       int sm_count, cudaStream_t st);
 // dense path, alpha != 0: thread-per-gene elastic-net CD with the shared Gram UtU (k_cd_dense.cu). `order` (optional) maps
 // thread slots to genes; `sweeps_per_gene` (optional) receives every gene's sweep count.
+// `table`: scratch of cd_dense_table_elems() doubles; resident_all: the 200-register variant (10 one-warp blocks per SM) instead of
+// the 255-register one (8 per SM, faster sweeps).
+size_t cd_dense_table_elems();
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
-                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, cudaStream_t st);
+                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, double* table,
+                     bool resident_all, cudaStream_t st);
 // order[] for the next launch_cd_dense from the sweep counts of the last one (descending, bucketed)
 // (`work`: cd_order_work_ints() ints, zero-initialised once; the kernel leaves it zeroed)
 size_t cd_order_work_ints();
 void launch_cd_order(const int* sweeps_per_gene, int64_t P, int* order, int* work, const uint32_t* als_iter, cudaStream_t st);
 void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xty, const double* w0, double lambda, double alpha, double tol,
                            int perm_mode, uint64_t seed, uint32_t als_iter, double* beta, int* sweeps, const unsigned char* perm_table,
-                           cudaStream_t st);
+                           double* table, cudaStream_t st);
 // stand-alone batched solver (insider_b200_strong_cd): XtX column-major K x K, either shared or per column [n][K*K]
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,

@@ -140,6 +140,7 @@ struct insider_session {
     int* sweeps_gene = nullptr;          // dense CD: sweeps of every local gene in the last iteration
     int* cd_order = nullptr;             // dense CD: slot -> gene, sorted by the last iteration's sweep counts
     int* cd_order_work = nullptr;
+    double* cd_table = nullptr;          // dense CD: XtX table prepared once per column update
     int* err_dev = nullptr;
     uint32_t max_records = 0, n_records = 0;
     uint32_t iter = 0;
@@ -149,8 +150,11 @@ struct insider_session {
     double loop_ms = 0, h2d = 0, d2h = 0;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaGraphExec_t iter_graph = nullptr;   // one ALS iteration (run_iteration + k_bump_iter), replayed
-    int64_t launches_per_iter = 0;
+    // one ALS iteration (run_iteration + k_bump_iter), replayed. Two variants: [0] the first iterations (hundreds to thousands of
+    // CD sweeps per gene: fastest sweep), [1] afterwards (a few sweeps per gene: all blocks of the dense solver resident at once)
+    cudaGraphExec_t iter_graphs[2] = {nullptr, nullptr};
+    int64_t launches_per_iter_v[2] = {0, 0};
+    int graph_variant = 0;
     bool graph_failed = false;
     std::vector<ProfEntry> prof;
     std::map<std::string, std::pair<double, int64_t>> prof_acc;
@@ -475,8 +479,9 @@ void run_iteration(insider_session* s) {
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
     if (!s->masked && s->opt.alpha != 0.0) {
         { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
-        Launch l(s, "k_cd_dense");
-        launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, st);
+        Launch l(s, "k_cd_dense", 2);
+        launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
+                        s->graph_variant == 1, st);
     } else {
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
@@ -573,6 +578,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->sweeps_gene = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
         s->cd_order = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
         s->cd_order_work = s->pool.get<int>(cd_order_work_ints(), true, st);
+        s->cd_table = s->pool.get<double>(cd_dense_table_elems(), true, st);
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
         upload_factors(s, f);
@@ -583,16 +589,22 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
     return s;
 }
 
+// ALS iteration from which the dense solver runs with all its blocks resident (see k_cd_dense.cu): by then a gene needs tens of
+// sweeps, not thousands
+constexpr uint32_t CD_VARIANT_SWITCH_ITER = 24;
+
 // one iteration + iteration-counter bump, replayed as a CUDA graph unless per-kernel profiling is on
 void launch_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
+    const int v = (s->iter >= CD_VARIANT_SWITCH_ITER) ? 1 : 0;
+    s->graph_variant = v;
     const bool want_graph = s->opt.use_graph >= 0 && !s->ctx->profile && !s->graph_failed;
     if (!want_graph) {
         run_iteration(s);
         { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
         return;
     }
-    if (!s->iter_graph) {
+    if (!s->iter_graphs[v]) {
         const int64_t before = s->launches;
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
@@ -601,19 +613,19 @@ void launch_iteration(insider_session* s) {
             launch_bump_iter(s->state, st); s->launches += 1;
         } catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         cudaError_t e = cudaStreamEndCapture(st, &graph);
-        s->launches_per_iter = s->launches - before;
+        s->launches_per_iter_v[v] = s->launches - before;
         s->launches = before;
-        if (e == cudaSuccess) e = cudaGraphInstantiate(&s->iter_graph, graph, 0);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&s->iter_graphs[v], graph, 0);
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess) {                       // fall back to plain launches (still the CUDA path)
-            cudaGetLastError(); s->iter_graph = nullptr; s->graph_failed = true;
+            cudaGetLastError(); s->iter_graphs[v] = nullptr; s->graph_failed = true;
             run_iteration(s);
             { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
             return;
         }
     }
-    CUDA_TRY(cudaGraphLaunch(s->iter_graph, st));
-    s->launches += s->launches_per_iter;
+    CUDA_TRY(cudaGraphLaunch(s->iter_graphs[v], st));
+    s->launches += s->launches_per_iter_v[v];
 }
 
 void do_step(insider_session* s, uint32_t n_iters, int32_t* done, double* ms) {
@@ -658,7 +670,7 @@ void fill_result(insider_session* s, insider_result* res) {
 void destroy_session(insider_session* s) {
     if (!s) return;
     for (auto& p : s->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
-    if (s->iter_graph) cudaGraphExecDestroy(s->iter_graph);
+    for (auto& ge : s->iter_graphs) if (ge) cudaGraphExecDestroy(ge);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -853,7 +865,10 @@ int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const do
         CUDA_TRY(cudaMemcpyAsync(dG, XtX, gsz * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dx, Xty, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(dw, wstart, (size_t)K * n_cols * 8, cudaMemcpyHostToDevice, st));
-        if (shared_gram) launch_cd_dense_batch(K, n_cols, dG, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, db, dsw, ctx->perm_table, st);
+        if (shared_gram) {
+            double* dtab = pool.get<double>(cd_dense_table_elems(), false);
+            launch_cd_dense_batch(K, n_cols, dG, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, db, dsw, ctx->perm_table, dtab, st);
+        }
         else launch_cd_batch(K, n_cols, dG, false, dx, dw, lambda, alpha, tol, perm_mode, seed, als_iter, gene0, db, dsw, dq, ctx->perm_table, ctx->sm_count, st);
         CUDA_TRY(cudaMemcpyAsync(beta, db, (size_t)K * n_cols * 8, cudaMemcpyDeviceToHost, st));
         if (sweeps) CUDA_TRY(cudaMemcpyAsync(sweeps, dsw, (size_t)n_cols * 4, cudaMemcpyDeviceToHost, st));

@@ -224,7 +224,8 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
         r->Y = r->pool.get<double>(y_elems, true, st);
         if (r->Pl > 0) {
             // contiguous H2D into a staging buffer in column chunks, re-pitched on the device
-            const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(r->Pl, (int64_t)((size_t)256 << 20) / ((size_t)N * 8)));
+            // (32 MB staging: a large one-off allocation would cost more in memory-pool growth than the copy itself)
+            const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(r->Pl, (int64_t)((size_t)32 << 20) / ((size_t)N * 8)));
             double* stage = nullptr;
             CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)chunk * N * 8, st));
             for (int64_t c0 = 0; c0 < r->Pl; c0 += chunk) {

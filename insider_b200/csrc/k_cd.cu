@@ -14,11 +14,14 @@
 // re-admission test (coordinate_descent.cpp:118-119) is |q_e| > alpha lambda for excluded e because beta_e = 0 there.
 // Visit order: counter-based permutation identical to the oracle's mode B.
 //
-// Mapping (k_cd_persistent): 8 lanes per gene, 4 genes per warp, lane li / slot s. Groups pull genes from an atomic
-// queue (sweep counts vary 4x between genes: static assignment left 35 % of the issue slots to finished groups).
-// Two register layouts: "coordinate layout" c = s*8 + li, and "position layout" where slot (s, li) holds the coordinate
-// visited at step i = s*8 + li of the current sweep, so the unrolled step loop has a compile-time owner lane/slot.
-// ncu history for this kernel is under profiles/ (r01_ncu_k_col_solve_*).
+// Mapping (k_cd_persistent): 8 lanes per gene, 4 genes per warp, lane li of a group holds q of coordinates li, li+8, li+16,
+// (li+24) in registers for the whole solve (coordinate layout; no per-sweep relayout). Groups pull genes from an atomic queue
+// (sweep counts vary 4x between genes) and run independently: each has its own sweep index and therefore its own visiting
+// order. A step for coordinate k: select the slot k>>3 (group-uniform), broadcast q_k from lane k&7 with one 64-bit shuffle,
+// every lane computes the same scalar update from the group's shared beta / diagonal arrays, then updates its own q with its
+// 3-4 elements of row k of the gene's Gram matrix (8 consecutive doubles per group: conflict-free). ~12 shared-memory
+// wavefronts per 4 gene-steps; the previous version (position layout re-built through shared memory every sweep, gathers of
+// permuted columns) spent 31 (profiles/r01_ncu_k_cd_persistent_v5_dense_A.txt).
 #include <algorithm>
 
 #include "common.cuh"
@@ -30,7 +33,7 @@ namespace {
 
 constexpr int LPG = 8;            // lanes per gene
 constexpr int GPW = 4;            // genes per warp
-constexpr int CD_WARPS = 4;       // warps per block
+constexpr int CD_WARPS = 2;       // warps per block (8 genes, 43 KB of per-gene tables at K = 23: 5 blocks = 40 genes per SM)
 constexpr int MAX_SWEEPS = 200000;
 
 __device__ __forceinline__ double grp_sum(double v) {
@@ -169,19 +172,17 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     const uint32_t gmask = 0xffu << grp_shift;
     double* Xall_s = reinterpret_cast<double*>(smem_raw);
     constexpr int n_mats = PERGENE ? CD_WARPS * GPW : 1;
-    double* sh_all = Xall_s + (size_t)n_mats * KP * XLD;                       // [CD_WARPS*GPW][5*KP]
-    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)CD_WARPS * GPW * 5 * KP);
+    double* sh_all = Xall_s + (size_t)n_mats * KP * XLD;                       // [CD_WARPS*GPW][3*KP]
+    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)CD_WARPS * GPW * 3 * KP);
     const int gslot = warp * GPW + grp;
     double* Xs = PERGENE ? Xall_s + (size_t)gslot * KP * XLD : Xall_s;
-    double* sh = sh_all + (size_t)gslot * 5 * KP;
+    double* sh = sh_all + (size_t)gslot * 3 * KP;
     unsigned char* ord_s = ord_all + gslot * 32;
-    double* Bc = sh; double* Qc = sh + KP; double* Dc = sh + 2 * KP; double* DENc = sh + 3 * KP; double* RDc = sh + 4 * KP;
+    double* Bc = sh; double* DRc = sh + KP;            // beta [KP] | (XtX_kk, 1/(XtX_kk + l2)) pairs [2*KP]   (16-byte aligned: KP % 8 == 0)
     const int K = a.K;
     const double tol = a.tol_dev ? *a.tol_dev : a.tol_host;
     const uint32_t als_iter = a.als_iter_dev ? *a.als_iter_dev : a.als_iter_host;
     const double la = a.lambda * a.alpha, l2 = a.lambda * (1.0 - a.alpha);
-    const double INF = __longlong_as_double(0x7ff0000000000000ll);
-    const uint32_t valid_mask = (K >= 32) ? 0xffffffffu : ((1u << K) - 1u);
     const uint64_t key_iter = mix64(a.seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter));   // perm_key(): first factor
 
     if (!PERGENE) {
@@ -191,15 +192,17 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         }
         __syncthreads();
     }
-    const uint32_t xbase = smem_u32(Xs);
 
     // per-group solver state
     int64_t gene = 0;
     bool active = false, retired = false;
     uint32_t inc = 0, draw = 0;
     int n_inc = 0, sweeps = 0;
-    uint32_t row_w = 0, row_draw = 0xffffffffu;                // prefetched permutation-table word (see below)
+    uint32_t row_w = 0, row_draw = 0xffffffffu;                // prefetched order-table word (see below)
     unsigned long long sweeps_acc = 0, steps_acc = 0;
+    double q[SL];                                              // q = X'y - X'X beta of coordinates s*8 + li
+#pragma unroll
+    for (int s = 0; s < SL; ++s) q[s] = 0.0;
 
     while (true) {
         // ---- claim and set up a new gene (divergent per group; group-local masks only)
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     }
                     __syncwarp(gmask);
                 }
-                double xty[SL], beta[SL], q[SL];
+                double xty[SL], beta[SL];
                 double mx = 0.0;
 #pragma unroll
                 for (int s = 0; s < SL; ++s) {
@@ -265,8 +268,8 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
 #pragma unroll
                 for (int s = 0; s < SL; ++s) {
                     const int c = s * LPG + li;
-                    const double d = Xs[c * XLD + c], den = d + l2;
-                    Bc[c] = beta[s]; Qc[c] = q[s]; Dc[c] = d; DENc[c] = den; RDc[c] = 1.0 / den;
+                    const double d = Xs[c * XLD + c];
+                    Bc[c] = beta[s]; DRc[2 * c] = d; DRc[2 * c + 1] = 1.0 / (d + l2);
                 }
                 __syncwarp(gmask);
                 n_inc = __popc(inc); draw = 0; sweeps = 0; active = true; row_draw = 0xffffffffu;
@@ -274,127 +277,75 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         }
         if (__all_sync(FULL, retired)) break;
 
-        // ---- visiting order (coordinate_descent.cpp:89): position of every coordinate in this sweep. Active coordinates take
-        //      the permutation selected from the table by the per-sweep key; inactive ones keep ascending order behind them.
-        int pos[SL];
+        // ---- visiting order of this group's sweep (coordinate_descent.cpp:89): the per-sweep key selects a table permutation of
+        //      all K coordinates (shared by every gene at this sweep index); active coordinates are visited in that order. Lane
+        //      li holds 4-byte word li of the 32-byte order row; the row of the NEXT sweep is prefetched one sweep ahead.
         {
-            // The per-sweep key selects a table permutation of all K coordinates (shared by every gene at this sweep index);
-            // lane li holds 4-byte word li of its 32-byte rank row. The row of the NEXT sweep is prefetched one sweep ahead.
-            auto row_word = [&](uint32_t dr) -> const uint32_t* {
+            auto row_word = [&](uint32_t dr) -> uint32_t {
+                if (a.perm_mode != 1) { const uint32_t c0 = 4u * li; return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24); }
                 const uint64_t pk = key_iter ^ mix64((uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
-                return reinterpret_cast<const uint32_t*>(a.perm_table + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + li;
+                return __ldg(reinterpret_cast<const uint32_t*>(a.perm_table + PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + li);
             };
-            if (row_draw != draw) row_w = __ldg(row_word(draw));                          // new gene
-            // rank of every own coordinate in the full order; A = set of ranks taken by active coordinates
-            int rk[SL];
-            uint32_t A = 0;
-#pragma unroll
-            for (int s = 0; s < SL; ++s) {
-                const int c = s * LPG + li;
-                const uint32_t w = __shfl_sync(FULL, row_w, c >> 2, LPG);
-                rk[s] = (a.perm_mode == 1) ? (int)((w >> (8 * (c & 3))) & 0xffu) : c;
-                if ((inc >> c) & 1u) A |= 1u << rk[s];
-            }
-            A |= __shfl_xor_sync(FULL, A, 4); A |= __shfl_xor_sync(FULL, A, 2); A |= __shfl_xor_sync(FULL, A, 1);
-#pragma unroll
-            for (int s = 0; s < SL; ++s) {
-                const int c = s * LPG + li;
-                const uint32_t below = (1u << c) - 1u;
-                const bool on = (inc >> c) & 1u;
-                // active: rank among the active coordinates; inactive ones keep ascending order behind them
-                pos[s] = on ? __popc(A & ((1u << rk[s]) - 1u)) : ((c < K) ? n_inc + __popc(~inc & valid_mask & below) : c);
-            }
-            row_w = __ldg(row_word(draw + 1)); row_draw = draw + 1;                       // consumed by the next sweep
+            if (row_draw != draw) row_w = row_word(draw);                                 // new gene
+            reinterpret_cast<uint32_t*>(ord_s)[li] = row_w;
+            row_w = row_word(draw + 1); row_draw = draw + 1;                              // consumed by the next sweep
         }
         ++draw;
         __syncwarp();
-#pragma unroll
-        for (int s = 0; s < SL; ++s) ord_s[pos[s]] = (unsigned char)(s * LPG + li);
-        __syncwarp();
-        // ---- gather into position layout; positions >= n_on get an infinite threshold (their update is exactly 0)
-        const int n_on = active ? n_inc : 0;
-        int nmax = n_on;
-        nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 8));
-        nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 16));
-        uint32_t cdo[SL]; int rowoff[SL], cd[SL];
-        double b[SL], q[SL], d[SL], den[SL], rd[SL], lap[SL], upsave[SL];
-#pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            const int c = ord_s[s * LPG + li];
-            cd[s] = c; b[s] = Bc[c]; q[s] = Qc[c]; d[s] = Dc[c]; den[s] = DENc[c]; rd[s] = RDc[c];
-            upsave[s] = 0.0;
-            lap[s] = (s * LPG + li < n_on) ? la : INF;
-            cdo[s] = xbase + (uint32_t)c * 8u;
-            rowoff[s] = c * XLD * 8;
-        }
-        // ---- one sweep; step i is owned by lane (i & 7), slot (i >> 3). The XtX row of step i+1 does not depend on the
-        //      update chain, so it is fetched one step ahead (its shared-memory latency hides behind the chain of step i).
-        double xv[SL];
-        {
-            const uint32_t ro0 = (uint32_t)__shfl_sync(FULL, rowoff[0], 0, LPG);
-#pragma unroll
-            for (int s = 0; s < SL; ++s) xv[s] = lds64(ro0 + cdo[s]);
-        }
-#pragma unroll
-        for (int i = 0; i < KP; ++i) {
-            if (i >= nmax) break;
-            const int si = i >> 3, ow = i & 7;
-            double xn[SL];
-            if (i + 1 < KP) {
-                const uint32_t ron = (uint32_t)__shfl_sync(FULL, rowoff[(i + 1) >> 3], (i + 1) & 7, LPG);
-#pragma unroll
-                for (int s = 0; s < SL; ++s) xn[s] = lds64(ron + cdo[s]);
-            }
-            const double bo = b[si];
-            const double up = fma(bo, d[si], q[si]);                             // :94
-            const double t1 = fabs(up) - lap[si];
-            // :99-104, branch-free: correctly rounded copysign(t1, up) / den (reciprocal + Markstein), 0 when t1 <= 0.
-            // Positions beyond n_on hold excluded coordinates (beta = 0) and have lap = INF: t1 = -INF -> nb = 0 -> dlt = 0.
-            const double num = copysign(t1, up);
-            double nb = num * rd[si];
-            nb = fma(fma(-den[si], nb, num), rd[si], nb);
-            nb = (t1 > 0.0) ? nb : 0.0;
-            const double dlt = nb - bo;
-            const double dkk = __shfl_sync(FULL, dlt, ow, LPG);
-            if (li == ow) { b[si] = nb; upsave[si] = up; }                        // :106-109 (loss decrement: after the sweep)
-#pragma unroll
-            for (int s = 0; s < SL; ++s) q[s] = fma(-dkk, xv[s], q[s]);
-            if (i + 1 < KP) {
-#pragma unroll
-                for (int s = 0; s < SL; ++s) xv[s] = xn[s];
-            }
-        }
-        // ---- loss change of the sweep, dL = sum_k (new-old)((XtX_kk + l2)(new+old)/2 - upper_k) + lambda alpha(|new|-|old|),
-        //      evaluated for all slots at once (Bc still holds the pre-sweep values); then scatter back to coordinate layout
+        // ---- one sweep: step i visits coordinate k = ord[i] of every group (groups are at different sweeps: k differs per group)
+        const uint32_t incs = active ? inc : 0u;                                          // finished / retired groups: all steps are no-ops
         double dl = 0.0;
+        int k = ord_s[0];
+        for (int i = 0; i < K; ++i) {
+            const int kn = ord_s[(i + 1 < K) ? i + 1 : i];
+            const int sk = k >> 3, ok = k & 7;
+            // the gene's row k (8 consecutive doubles per slot and group) and the group's scalars of coordinate k
+            double xr[SL];
 #pragma unroll
-        for (int s = 0; s < SL; ++s) {
-            const double b0 = Bc[cd[s]];
-            dl = fma(b[s] - b0, fma(0.5 * den[s], b[s] + b0, -upsave[s]), dl);
-            dl = fma(la, fabs(b[s]) - fabs(b0), dl);
+            for (int s = 0; s < SL; ++s) xr[s] = Xs[k * XLD + s * LPG + li];
+            const double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);            // XtX_kk, 1/(XtX_kk + l2)
+            const double bo = Bc[k];
+            double qsel = q[0];
+#pragma unroll
+            for (int s = 1; s < SL; ++s) qsel = (sk == s) ? q[s] : qsel;
+            const double qk = __shfl_sync(FULL, qsel, ok, LPG);
+            const bool on = (incs >> k) & 1u;
+            const double den = dr.x + l2;
+            const double up = fma(bo, dr.x, qk);                                          // :94
+            const double t1 = fabs(up) - la;
+            const double num = copysign(t1, up);
+            double nb = num * dr.y;                                                       // :99-104, correctly rounded num / den
+            nb = fma(fma(-den, nb, num), dr.y, nb);
+            nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
+            nb = on ? nb : bo;                                                            // excluded coordinate / idle group: no-op
+            const double dlt = nb - bo;
+            // exact loss decrement: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
+            dl = fma(dlt, fma(0.5 * den, nb + bo, -up), dl);
+            dl = fma(la, fabs(nb) - fabs(bo), dl);
+            if (li == ok) Bc[k] = nb;                                                     // :106-109
+            const double nd = -dlt;
+#pragma unroll
+            for (int s = 0; s < SL; ++s) q[s] = fma(nd, xr[s], q[s]);
+            k = kn;
         }
         __syncwarp();
-#pragma unroll
-        for (int s = 0; s < SL; ++s) { Bc[cd[s]] = b[s]; Qc[cd[s]] = q[s]; }
-        const double delta = grp_sum(dl);
-        // inner do-while ends (:114) -> KKT check on the excluded set (:118-124)
-        const bool inner_end = active && (!(fabs(delta) > tol) || sweeps + 1 >= MAX_SWEEPS);
+        // inner do-while ends (:114) -> KKT check on the excluded set (:118-124); every lane of the group holds the same dl
+        const bool inner_end = active && (!(fabs(dl) > tol) || sweeps + 1 >= MAX_SWEEPS);
         uint32_t vmask = 0;
         if (inner_end) {
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
-                const int i = s * LPG + li;
-                if (i >= n_inc && cd[s] < K && fabs(q[s]) > la) vmask |= 1u << cd[s];
+                const int c = s * LPG + li;
+                if (c < K && !((inc >> c) & 1u) && fabs(q[s]) > la) vmask |= 1u << c;     // |XtX[e,inc] beta - Xty_e| = |q_e| (beta_e = 0)
             }
         }
         vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
         if (active) {
             ++sweeps;
-            steps_acc += (unsigned long long)n_on;      // coordinate updates attempted (statistics only)
+            steps_acc += (unsigned long long)n_inc;     // coordinate updates attempted (statistics only)
             if (inner_end) {
                 if (vmask == 0u || sweeps >= MAX_SWEEPS) {
-                    // finished: write the gene back (coordinate layout)
-                    __syncwarp(gmask);
+                    // finished: write the gene back
 #pragma unroll
                     for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = Bc[c]; }
                     if (li == 0) { sweeps_acc += (unsigned long long)sweeps; if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps; }
@@ -467,7 +418,7 @@ void opt_in_smem(KernelT k, size_t bytes) {
 
 size_t cd_smem_bytes(int KP, bool pergene) {
     const size_t mats = pergene ? (size_t)CD_WARPS * GPW : 1;
-    return mats * KP * (KP + 1) * 8 + (size_t)CD_WARPS * GPW * 5 * KP * 8 + CD_WARPS * GPW * 32;
+    return mats * KP * (KP + 1) * 8 + (size_t)CD_WARPS * GPW * 3 * KP * 8 + CD_WARPS * GPW * 32;
 }
 
 void launch_cd(const CdArgs& a, int KP, bool pergene, int sm_count, cudaStream_t st) {

@@ -425,7 +425,7 @@ void launch_cd(const CdArgs& a, int KP, bool pergene, int sm_count, cudaStream_t
     const size_t smem = cd_smem_bytes(KP, pergene);
     const int64_t genes_per_block = CD_WARPS * GPW;
     int64_t blocks = (a.P + genes_per_block - 1) / genes_per_block;
-    int per_sm = (int)std::min<size_t>(8, (227 * 1024) / (smem + 1024));      // persistent: enough blocks to fill every SM
+    int per_sm = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));      // persistent: enough blocks to fill every SM
     if (per_sm < 1) per_sm = 1;
     blocks = std::min<int64_t>(blocks, (int64_t)sm_count * per_sm);
     cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), st);

@@ -393,12 +393,11 @@ void launch_kt(const CdDenseArgs& a, cudaStream_t st) {
     kern<<<blocks, DW * 32, smem, st>>>(a);
 }
 
-// `table`: device buffer of cd_dense_table_elems() doubles (filled here); resident_all: prefer the variant whose blocks all fit at once
-void launch(CdDenseArgs a, double* table, bool resident_all, cudaStream_t st) {
+// `table`: prepared by launch_cd_dense_table(); resident_all: prefer the variant whose blocks all fit at once
+void launch(CdDenseArgs a, const double* table, bool resident_all, cudaStream_t st) {
     a.la = a.lambda * a.alpha; a.l2 = a.lambda * (1.0 - a.alpha);
     if (a.P <= 0) return;
     const int KT = (a.K + 3) / 4 * 4;
-    k_cd_table<<<1, 256, 0, st>>>(a.XtX, a.xs_r, a.xs_c, a.K, KT, a.l2, table);
     a.table = table;
 #define LAUNCH_KT(KTv) if (resident_all) launch_kt<KTv, 10>(a, st); else launch_kt<KTv, 8>(a, st); break;
     switch (KT / 4) {
@@ -417,9 +416,12 @@ void launch(CdDenseArgs a, double* table, bool resident_all, cudaStream_t st) {
 }  // namespace
 
 size_t cd_dense_table_elems() { return (size_t)32 * 36; }
+void launch_cd_dense_table(int K, const double* XtX, int xs_r, int xs_c, double lambda, double alpha, double* table, cudaStream_t st) {
+    k_cd_table<<<1, 256, 0, st>>>(XtX, xs_r, xs_c, K, (K + 3) / 4 * 4, lambda * (1.0 - alpha), table);
+}
 
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
-                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, double* table,
+                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, const double* table,
                      bool resident_all, cudaStream_t st) {
     CdDenseArgs a{};
     a.XtX = UtU; a.xs_r = g.KP; a.xs_c = 1;
@@ -442,6 +444,7 @@ void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xt
     a.Xty = Xty; a.W0 = w0; a.Vout = beta; a.ldv = K; a.K = K; a.P = n;
     a.lambda = lambda; a.alpha = alpha; a.tol_dev = nullptr; a.tol_host = tol; a.als_iter_dev = nullptr; a.als_iter_host = als_iter;
     a.seed = seed; a.perm_mode = perm_mode; a.sweeps_per_gene = sweeps; a.perm_table = perm_table;
+    launch_cd_dense_table(K, XtX, 1, K, lambda, alpha, table, st);
     launch(a, table, false, st);
 }
 

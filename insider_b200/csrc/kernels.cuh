@@ -101,11 +101,13 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
                       int sm_count, cudaStream_t st);
 // dense path, alpha != 0: thread-per-gene elastic-net CD with the shared Gram UtU (k_cd_dense.cu). `order` (optional) maps
 // thread slots to genes; `sweeps_per_gene` (optional) receives every gene's sweep count.
-// `table`: scratch of cd_dense_table_elems() doubles; resident_all: the 200-register variant (10 one-warp blocks per SM) instead of
-// the 255-register one (8 per SM, faster sweeps).
+// `table`: cd_dense_table_elems() doubles filled by launch_cd_dense_table() from UtU (independent of Xty: may run beside
+// k_col_xty); resident_all: the 200-register variant (10 one-warp blocks per SM) instead of the 255-register one (8 per SM,
+// faster sweeps).
 size_t cd_dense_table_elems();
+void launch_cd_dense_table(int K, const double* XtX, int xs_r, int xs_c, double lambda, double alpha, double* table, cudaStream_t st);
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
-                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, double* table,
+                     unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, const double* table,
                      bool resident_all, cudaStream_t st);
 // order[] for the next launch_cd_dense from the sweep counts of the last one (descending, bucketed)
 // (`work`: cd_order_work_ints() ints, zero-initialised once; the kernel leaves it zeroed)

@@ -83,6 +83,7 @@ struct DevPool {                       // frees everything it handed out
 struct insider_ctx {
     int device = 0, sm_count = 148, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;            // second stream: small independent kernels of an iteration run beside the main chain
     ncclComm_t comm = nullptr;
     bool profile = false;
     unsigned char* perm_table = nullptr;    // rank tables of the counter-based permutation source (common.cuh)
@@ -150,6 +151,7 @@ struct insider_session {
     double loop_ms = 0, h2d = 0, d2h = 0;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};   // fork/join of the side stream
     // one ALS iteration (run_iteration + k_bump_iter), replayed. Two variants: [0] the first iterations (hundreds to thousands of
     // CD sweeps per gene: fastest sweep), [1] afterwards (a few sweeps per gene: all blocks of the dense solver resident at once)
     cudaGraphExec_t iter_graphs[2] = {nullptr, nullptr};
@@ -427,6 +429,16 @@ void evaluate(insider_session* s, bool initial) {
 }
 
 // ---- one ALS iteration (src/optimize.cpp:331-378) -------------------------------------------------------------------
+// Side-stream sections: small kernels that do not depend on each other run beside the main chain (also inside the captured
+// graph, where they become parallel branches). With per-kernel profiling on everything stays on the main stream.
+struct SideSection {
+    insider_session* s; int idx; cudaStream_t side;
+    SideSection(insider_session* s_, int i) : s(s_), idx(i), side(s_->ctx->profile ? s_->ctx->stream : s_->ctx->side) {
+        if (side != s->ctx->stream) { cudaEventRecord(s->ev_fork[idx], s->ctx->stream); cudaStreamWaitEvent(side, s->ev_fork[idx], 0); }
+    }
+    void join() { if (side != s->ctx->stream) { cudaEventRecord(s->ev_join[idx], side); cudaStreamWaitEvent(s->ctx->stream, s->ev_join[idx], 0); } }
+};
+
 void run_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
     insider_resident* r = s->r;
@@ -445,10 +457,13 @@ void run_iteration(insider_session* s) {
     }
     if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->stats, s->stats, s->stats_elems, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(stats)");
     // normal-equation matrices of every level of every confounder: assembled and factorised once (they do not depend on A)
+    SideSection sec0(s, 0);                // dense path: the per-level sums of B run beside the factorisations
     if (r->C > 0) {
         if (s->masked) { Launch l(s, "k_level_gram"); launch_level_gram(g, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->D, s->GLp, st); }
+        if (!s->masked) { Launch l(s, "k_level_sumB"); launch_level_sumB(g, s->tab_dev, s->total_levels, s->B, s->SB, sec0.side); }
         { Launch l(s, "k_level_factor"); launch_level_factor(g, s->masked, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, st); }
     }
+    sec0.join();
     // Gauss-Seidel over confounder blocks (:335-362)
     if (s->masked) {
         for (int c = 0; c < r->C; ++c) {
@@ -459,7 +474,6 @@ void run_iteration(insider_session* s) {
     } else if (r->C > 0) {
         // dense path: per-level sums of B once, then all C block updates in one single-block launch on factor-sized data
         DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
-        { Launch l(s, "k_level_sumB"); launch_level_sumB(g, s->tab_dev, s->total_levels, s->B, s->SB, st); }
         { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs(g, dg, r->C, r->Q, s->total_levels, s->A_all, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->SB, s->G, s->Lfac, st); }
         if (r->inc_continuous) {   // the continuous block below works on the row factor: rebuild it with the new A_c
             Launch l(s, "k_build_u", 2);
@@ -475,12 +489,18 @@ void run_iteration(insider_session* s) {
     }
     // row factor rebuild (:365-373) and column update (:376)
     { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
+    const bool dense_cd = !s->masked && s->opt.alpha != 0.0;
+    SideSection sec1(s, 1);                // dense elastic net: slot order and XtX table (neither needs Xty) beside the pass over Y
+    if (dense_cd) {
+        { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, sec1.side); }
+        { Launch l(s, "k_cd_table"); launch_cd_dense_table(g.K, s->UtU, g.KP, 1, s->opt.lambda2, s->opt.alpha, s->cd_table, sec1.side); }
+    }
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
+    sec1.join();
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
-    if (!s->masked && s->opt.alpha != 0.0) {
-        { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
-        Launch l(s, "k_cd_dense", 2);
+    if (dense_cd) {
+        Launch l(s, "k_cd_dense");
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
                         s->graph_variant == 1, st);
     } else {
@@ -582,6 +602,10 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->cd_table = s->pool.get<double>(cd_dense_table_elems(), true, st);
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
+        }
         upload_factors(s, f);
         // initial row factor and evaluation (:286-289, :320-323)
         { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
@@ -673,6 +697,7 @@ void destroy_session(insider_session* s) {
     for (auto& p : s->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto& ge : s->iter_graphs) if (ge) cudaGraphExecDestroy(ge);
     if (s->ev0) cudaEventDestroy(s->ev0);
+    for (int i = 0; i < 2; ++i) { if (s->ev_fork[i]) cudaEventDestroy(s->ev_fork[i]); if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]); }
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
 }
@@ -699,6 +724,7 @@ int create_ctx(insider_ctx** out, int device, int rank, int world, const void* i
         c->device = device; c->sm_count = prop.multiProcessorCount; c->rank = rank; c->world = world;
         try {
             CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
             {
                 std::vector<unsigned char> tab(PERM_TABLE_BYTES);
                 build_perm_table(tab.data());
@@ -715,7 +741,7 @@ int create_ctx(insider_ctx** out, int device, int rank, int world, const void* i
                 ncclUniqueId uid; memcpy(&uid, id, sizeof(uid));
                 nccl_check(g_nccl.CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
             }
-        } catch (...) { if (c->perm_table) cudaFree(c->perm_table); if (c->stream) cudaStreamDestroy(c->stream); delete c; throw; }
+        } catch (...) { if (c->perm_table) cudaFree(c->perm_table); if (c->side) cudaStreamDestroy(c->side); if (c->stream) cudaStreamDestroy(c->stream); delete c; throw; }
         *out = c;
     });
 }
@@ -757,6 +783,7 @@ void insider_b200_ctx_destroy(insider_ctx* c) {
     cudaSetDevice(c->device);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->perm_table) cudaFree(c->perm_table);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

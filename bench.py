@@ -274,7 +274,7 @@ def run_ours(args, w, rank, world, local):
                        "timed_iterations": f"0..{args.steps - 1} from N(0,0.001^2) init", "parallelism": f"gene-sharded x{world}",
                        "l2": "Y (134 MB) exceeds L2 at N=1; at N>1 the shard is L2-resident in the real fit too (no flush between iterations)"},
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": oe["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y"},
+                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "device_loop_seconds": oe["loop_ms"] * 1e-3, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y"},
             "gpu_launches": int(out["kernel_launches"]),
             "clocks": sampler.summary(),
             "roofline": roof_dom or roof_iter,

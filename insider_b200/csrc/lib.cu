@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -84,6 +85,7 @@ struct insider_ctx {
     int device = 0, sm_count = 148, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;            // second stream: small independent kernels of an iteration run beside the main chain
+    bool no_side = false;                   // INSIDER_B200_NO_SIDE_STREAM=1: everything on the main stream (debugging)
     ncclComm_t comm = nullptr;
     bool profile = false;
     unsigned char* perm_table = nullptr;    // rank tables of the counter-based permutation source (common.cuh)
@@ -433,7 +435,7 @@ void evaluate(insider_session* s, bool initial) {
 // graph, where they become parallel branches). With per-kernel profiling on everything stays on the main stream.
 struct SideSection {
     insider_session* s; int idx; cudaStream_t side;
-    SideSection(insider_session* s_, int i) : s(s_), idx(i), side(s_->ctx->profile ? s_->ctx->stream : s_->ctx->side) {
+    SideSection(insider_session* s_, int i) : s(s_), idx(i), side((s_->ctx->profile || s_->ctx->no_side) ? s_->ctx->stream : s_->ctx->side) {
         if (side != s->ctx->stream) { cudaEventRecord(s->ev_fork[idx], s->ctx->stream); cudaStreamWaitEvent(side, s->ev_fork[idx], 0); }
     }
     void join() { if (side != s->ctx->stream) { cudaEventRecord(s->ev_join[idx], side); cudaStreamWaitEvent(s->ctx->stream, s->ev_join[idx], 0); } }
@@ -725,6 +727,7 @@ int create_ctx(insider_ctx** out, int device, int rank, int world, const void* i
         try {
             CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+            { const char* e = getenv("INSIDER_B200_NO_SIDE_STREAM"); c->no_side = e && e[0] == '1'; }
             {
                 std::vector<unsigned char> tab(PERM_TABLE_BYTES);
                 build_perm_table(tab.data());
@@ -855,12 +858,22 @@ int insider_b200_optimize_resident(insider_ctx* ctx, insider_resident* r, const 
 int insider_b200_optimize(insider_ctx* ctx, const insider_problem* prob, const insider_factors* fac, const insider_options* opt, insider_result* res,
                           char* errbuf, size_t errlen) {
     insider_resident* r = nullptr;
+    const bool trace = getenv("INSIDER_B200_TRACE") != nullptr;         // phase wall times of the one-shot call on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = insider_b200_upload(ctx, prob, &r, errbuf, errlen);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     const double up = r->h2d_bytes;
     rc = insider_b200_optimize_resident(ctx, r, fac, opt, res, errbuf, errlen);
     if (rc == INSIDER_OK && res) res->h2d_bytes += up;
+    const auto t2 = std::chrono::steady_clock::now();
     insider_b200_release(r);
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[insider_b200 rank %d] optimize: upload %.2f ms, fit %.2f ms (device loop %.2f ms), release %.2f ms\n", ctx->rank, ms(t0, t1),
+                ms(t1, t2), res ? res->loop_ms : 0.0, ms(t2, t3));
+    }
     return rc;
 }
 

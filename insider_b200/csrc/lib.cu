@@ -129,6 +129,7 @@ struct insider_session {
     double* XtXall = nullptr;           // masked path: per-gene Gram matrices [P_l][KP*KP]
     unsigned int* queue = nullptr;      // gene queue of the persistent CD kernel
     double* Vfull = nullptr;            // world > 1: gathered V for the final download
+    double* Vpack = nullptr;            // world > 1: the same without pitch (K x P contiguous)
     std::vector<int> lfac_base;         // first level-table index of each confounder
     int total_levels = 0, max_chunks = 1;
     LevelTable* tab_dev = nullptr;
@@ -383,7 +384,8 @@ void download_factors(insider_session* s, const insider_factors* f) {
             if (n == 0) continue;
             nccl_check(g_nccl.Broadcast(s->V, s->Vfull + (size_t)j0 * s->g.ldV, (size_t)n * s->g.ldV, NCCL_FLOAT64, rk, s->ctx->comm, st), "ncclBroadcast(V)");
         }
-        CUDA_TRY(cudaMemcpy2DAsync(f->column_factor, (size_t)K * 8, s->Vfull, (size_t)s->g.ldV * 8, (size_t)K * 8, (size_t)r->P, cudaMemcpyDeviceToHost, st));
+        launch_repitch(s->Vpack, K, s->Vfull, s->g.ldV, K, r->P, st);          // contiguous K x P, one download
+        CUDA_TRY(cudaMemcpyAsync(f->column_factor, s->Vpack, (size_t)r->P * K * 8, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int c = 0; c < s->n_factors; ++c) {
@@ -584,7 +586,7 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             s->GLp = s->pool.get<double>(1, true, st);
         }
         if (r->inc_continuous) s->cont_scratch = s->pool.get<double>(continuous_scratch_elems(g), true, st);
-        if (ctx->world > 1) s->Vfull = s->pool.get<double>((size_t)r->P * g.ldV, true, st);
+        if (ctx->world > 1) { s->Vfull = s->pool.get<double>((size_t)r->P * g.ldV, true, st); s->Vpack = s->pool.get<double>((size_t)r->P * f->K, false, st); }
         for (int c = 0; c < r->C; ++c) s->designs.push_back(RowDesign{r->L[c], r->level_of_row[c], r->rows_sorted[c], r->level_start[c], s->A_all + s->a_off[c]});
         s->designs_dev = s->pool.get<RowDesign>(std::max(1, r->C), true, st);
         if (r->C) CUDA_TRY(cudaMemcpyAsync(s->designs_dev, s->designs.data(), r->C * sizeof(RowDesign), cudaMemcpyHostToDevice, st));

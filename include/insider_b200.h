@@ -166,6 +166,10 @@ void insider_b200_set_profile(insider_ctx* ctx, int on);
  * do-while ran, src/coordinate_descent.cpp:86-114); n = number of entries of `out`, at most the context's local gene count.
  * Returns the number of entries written (0 when the last column update was a ridge solve or the masked solver). */
 int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n);
+/* optional hint for the dense elastic-net solver: expected sweep count of every local gene in the NEXT iteration (e.g. the
+ * counts of a previous fit of the same data). It only orders the work (genes with similar counts share a warp); results do
+ * not depend on it. Returns the number of entries taken. */
+int64_t insider_b200_als_hint_sweeps(insider_session* s, const int32_t* hint, int64_t n);
 
 /* batched single-column elastic-net solves (src/coordinate_descent.cpp:57-127). Problem b uses XtX[b] (K x K), Xty[b] (K),
  * wstart[b] (K); X and y of the reference signature are not needed in covariance form and are accepted as NULL.

@@ -19,7 +19,7 @@ EXPORTED = [
     "insider_b200_default_options", "insider_b200_version", "insider_b200_ctx_create", "insider_b200_nccl_unique_id",
     "insider_b200_ctx_create_dist", "insider_b200_ctx_destroy", "insider_b200_ctx_stream", "insider_b200_optimize",
     "insider_b200_upload", "insider_b200_release", "insider_b200_optimize_resident", "insider_b200_als_begin",
-    "insider_b200_als_step", "insider_b200_als_read", "insider_b200_als_end", "insider_b200_als_profile", "insider_b200_als_sweeps",
+    "insider_b200_als_step", "insider_b200_als_read", "insider_b200_als_end", "insider_b200_als_profile", "insider_b200_als_sweeps", "insider_b200_als_hint_sweeps",
     "insider_b200_set_profile", "insider_b200_strong_cd", "insider_b200_fit_interaction", "insider_b200_split",
     "insider_b200_tune_batch",
 ]
@@ -306,6 +306,12 @@ class Session:
         lib().insider_b200_als_sweeps.restype = C.c_int64
         got = lib().insider_b200_als_sweeps(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(n))
         return out[:got]
+
+    def hint_sweeps(self, hint) -> int:
+        """Expected sweep counts of the next iteration (orders the dense solver's work; results do not depend on it)."""
+        h = np.ascontiguousarray(hint, dtype=np.int32)
+        lib().insider_b200_als_hint_sweeps.restype = C.c_int64
+        return int(lib().insider_b200_als_hint_sweeps(self.h, h.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(h.size)))
 
     def end(self, read_factors: bool = True) -> dict:
         r, buf = make_result(int(self.opt.max_iter) // max(1, int(self.opt.check_every) or 10) + 3)

@@ -104,15 +104,27 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
 // `table`: cd_dense_table_elems() doubles filled by launch_cd_dense_table() from UtU (independent of Xty: may run beside
 // k_col_xty); resident_all: the 200-register variant (10 one-warp blocks per SM) instead of the 255-register one (8 per SM,
 // faster sweeps).
+// Phased execution: a launch runs sweeps [draw0, cap) of the genes it is given; genes that have not converged at sweep `cap`
+// are parked in `ps` (state in coordinate order) and taken up by the next launch (draw0 = that cap) in a new slot order
+// (launch_cd_order_parked). ps == nullptr, draw0 = 0, cap = 0xffffffff: one launch runs every gene to convergence.
+struct CdPhaseState {
+    double* state;      // [P][2 * round_up(K, 4)]
+    uint32_t* inc;      // [P]
+    float* dl;          // [P]
+    int* alive;         // [P]
+    int* n_slots;       // device scalar: parked genes = slots of the next phase
+};
 size_t cd_dense_table_elems();
 void launch_cd_dense_table(int K, const double* XtX, int xs_r, int xs_c, double lambda, double alpha, double* table, cudaStream_t st);
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
                      unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, const double* table,
-                     bool resident_all, cudaStream_t st);
+                     bool resident_all, const CdPhaseState* ps, uint32_t draw0, uint32_t cap, cudaStream_t st);
 // order[] for the next launch_cd_dense from the sweep counts of the last one (descending, bucketed)
 // (`work`: cd_order_work_ints() ints, zero-initialised once; the kernel leaves it zeroed)
 size_t cd_order_work_ints();
 void launch_cd_order(const int* sweeps_per_gene, int64_t P, int* order, int* work, const uint32_t* als_iter, cudaStream_t st);
+// order[] of the parked genes for the next phase (by the loss decrement of their last sweep) and their count in ps.n_slots
+void launch_cd_order_parked(const CdPhaseState& ps, int64_t P, int* order, int* work, const double* tol_dev, cudaStream_t st);
 void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xty, const double* w0, double lambda, double alpha, double tol,
                            int perm_mode, uint64_t seed, uint32_t als_iter, double* beta, int* sweeps, const unsigned char* perm_table,
                            double* table, cudaStream_t st);

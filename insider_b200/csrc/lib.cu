@@ -145,6 +145,9 @@ struct insider_session {
     int* cd_order = nullptr;             // dense CD: slot -> gene, sorted by the last iteration's sweep counts
     int* cd_order_work = nullptr;
     double* cd_table = nullptr;          // dense CD: XtX table prepared once per column update
+    CdPhaseState cd_phase{};             // dense CD: parked genes between the phases of a column update
+    int* cd_order_parked = nullptr;      // dense CD: slot order of a later phase
+    uint32_t cd_phase0 = 512;            // sweeps of the first phase (doubling afterwards)
     int* err_dev = nullptr;
     uint32_t max_records = 0, n_records = 0;
     uint32_t iter = 0;
@@ -155,10 +158,12 @@ struct insider_session {
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};   // fork/join of the side stream
-    // one ALS iteration (run_iteration + k_bump_iter), replayed. Two variants: [0] the first iterations (hundreds to thousands of
-    // CD sweeps per gene: fastest sweep), [1] afterwards (a few sweeps per gene: all blocks of the dense solver resident at once)
-    cudaGraphExec_t iter_graphs[2] = {nullptr, nullptr};
-    int64_t launches_per_iter_v[2] = {0, 0};
+    // one ALS iteration (run_iteration + k_bump_iter), replayed. Three variants of the dense elastic-net solve: [0] the first
+    // iterations (thousands of CD sweeps per gene, no useful prediction of the counts: phases with re-grouping), [1] the next
+    // ones (hundreds of sweeps, counts known from the previous iteration: one launch, fastest sweep), [2] afterwards (a few
+    // sweeps per gene: all blocks resident at once)
+    cudaGraphExec_t iter_graphs[3] = {nullptr, nullptr, nullptr};
+    int64_t launches_per_iter_v[3] = {0, 0, 0};
     int graph_variant = 0;
     bool graph_failed = false;
     std::vector<ProfEntry> prof;
@@ -503,10 +508,25 @@ void run_iteration(insider_session* s) {
     sec1.join();
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
-    if (dense_cd) {
+    if (dense_cd && s->graph_variant == 0) {
+        // first iterations (hundreds to thousands of sweeps per gene, counts spread 10x): phases of doubling length. A warp runs
+        // until its slowest gene is done, so after every phase the unconverged genes are re-grouped by how far they still are
+        // from the stopping rule: lane efficiency 0.47 -> 0.8 in iteration 0 (profiles/r01_cd_phases.txt). Launches whose
+        // phase has no gene left exit at once.
+        constexpr int N_PHASES = 9;
+        uint32_t draw0 = 0, cap = s->cd_phase0;
+        for (int ph = 0; ph < N_PHASES; ++ph) {
+            const bool last = ph == N_PHASES - 1;
+            if (ph > 0) { Launch l(s, "k_cd_order"); launch_cd_order_parked(s->cd_phase, g.P, s->cd_order_parked, s->cd_order_work, &s->state->tol, st); }
+            Launch l(s, "k_cd_dense");
+            launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, ph ? s->cd_order_parked : s->cd_order,
+                            s->ctx->perm_table, s->cd_table, false, &s->cd_phase, draw0, last ? 0xffffffffu : cap, st);
+            draw0 = cap; cap += std::max<uint32_t>(1u, cap / 2);                       // 512, 768, 1152, ... x1.5
+        }
+    } else if (dense_cd) {
         Launch l(s, "k_cd_dense");
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
-                        s->graph_variant == 1, st);
+                        s->graph_variant == 2, nullptr, 0u, 0xffffffffu, st);
     } else {
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
@@ -604,6 +624,16 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->cd_order = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
         s->cd_order_work = s->pool.get<int>(cd_order_work_ints(), true, st);
         s->cd_table = s->pool.get<double>(cd_dense_table_elems(), true, st);
+        {
+            const size_t Pn = (size_t)std::max<int64_t>(1, g.P);
+            s->cd_phase.state = s->pool.get<double>(Pn * 2 * (size_t)round_up(g.K, 4), false, st);
+            s->cd_phase.inc = s->pool.get<uint32_t>(Pn, true, st);
+            s->cd_phase.dl = s->pool.get<float>(Pn, true, st);
+            s->cd_phase.alive = s->pool.get<int>(Pn, true, st);
+            s->cd_phase.n_slots = s->pool.get<int>(1, true, st);
+            s->cd_order_parked = s->pool.get<int>(Pn, true, st);
+            if (const char* e = getenv("INSIDER_B200_CD_PHASE0")) { const long v = atol(e); if (v >= 1) s->cd_phase0 = (uint32_t)v; }
+        }
         s->err_dev = s->pool.get<int>(1, true, st);
         CUDA_TRY(cudaEventCreate(&s->ev0)); CUDA_TRY(cudaEventCreate(&s->ev1));
         for (int i = 0; i < 2; ++i) {
@@ -621,11 +651,14 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
 // ALS iteration from which the dense solver runs with all its blocks resident (see k_cd_dense.cu): by then a gene needs tens of
 // sweeps, not thousands
 constexpr uint32_t CD_VARIANT_SWITCH_ITER = 24;
+// ALS iterations that run the dense solver in phases (measured on the ageing-shaped fit: iteration 0 69 -> 44 ms, 1 and 2
+// -10 %, from iteration 3 on the previous iteration's counts order the work better than a mid-solve re-grouping)
+constexpr uint32_t CD_PHASED_ITERS = 3;
 
 // one iteration + iteration-counter bump, replayed as a CUDA graph unless per-kernel profiling is on
 void launch_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
-    const int v = (s->iter >= CD_VARIANT_SWITCH_ITER) ? 1 : 0;
+    const int v = (s->iter >= CD_VARIANT_SWITCH_ITER) ? 2 : (s->iter >= CD_PHASED_ITERS ? 1 : 0);
     s->graph_variant = v;
     const bool want_graph = s->opt.use_graph >= 0 && !s->ctx->profile && !s->graph_failed;
     if (!want_graph) {
@@ -840,6 +873,15 @@ int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n) {
     n = std::min<int64_t>(n, s->g.P);
     if (cudaSetDevice(s->ctx->device) != cudaSuccess) return 0;
     if (cudaMemcpyAsync(out, s->sweeps_gene, (size_t)n * 4, cudaMemcpyDeviceToHost, s->ctx->stream) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(s->ctx->stream) != cudaSuccess) return 0;
+    return n;
+}
+
+int64_t insider_b200_als_hint_sweeps(insider_session* s, const int32_t* hint, int64_t n) {
+    if (!s || !hint || n <= 0 || s->masked || s->opt.alpha == 0.0) return 0;
+    n = std::min<int64_t>(n, s->g.P);
+    if (cudaSetDevice(s->ctx->device) != cudaSuccess) return 0;
+    if (cudaMemcpyAsync(s->sweeps_gene, hint, (size_t)n * 4, cudaMemcpyHostToDevice, s->ctx->stream) != cudaSuccess) return 0;
     if (cudaStreamSynchronize(s->ctx->stream) != cudaSuccess) return 0;
     return n;
 }

@@ -243,14 +243,16 @@ def run_ours(args, w, rank, world, local):
         roof_dom = None
         if cd:
             note = ("thread-per-gene coordinate descent, K=23: every step needs the 24-double table row in every thread; ncu shows the "
-                    "shared-memory data pipe at 93 % of peak (l1tex__throughput) with the FP64 pipe at 38 %; lockstep warps run until their "
-                    "slowest gene converges (lane efficiency 0.47-0.85). See profiles/r01_ncu_k_cd_dense_v4_dense_A.txt"
+                    "shared-memory data pipe at 92 % of peak (l1tex__throughput) with the FP64 pipe at 42 %; lockstep warps run until their "
+                    "slowest gene converges (lane efficiency ~0.8 with phased re-grouping / ordering by the previous counts). "
+                    "See profiles/r01_ncu_k_cd_dense_v5_dense_A.txt, r01_cd_phases.txt"
                     if cd_name == "k_cd_dense" else
                     "8-lanes-per-gene coordinate descent with per-gene Gram matrices: bound by the shared-memory pipe; "
                     "see profiles/r01_ncu_k_cd_persistent_*.txt")
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture of this command's shape
-            # (profiles/r01_ncu_k_cd_dense_v4_dense_A.txt: 20.39 MB read, 0 written; algorithmic Xty + V = 18.6 MB)
-            traffic = 20393216 if (cd_name == "k_cd_dense" and world == 1 and args.workload == "ageing_full_377x44477_K23_fit") else None
+            # dram__bytes_read.sum + dram__bytes_write.sum of one whole-problem launch from the ncu --set full capture of this
+            # command's shape (profiles/r01_ncu_k_cd_dense_v5_dense_A.txt: 20.37 MB read, 0 written; algorithmic Xty + V = 18.6 MB;
+            # the phase launches of iterations 0-2 read their share of it)
+            traffic = 20372224 if (cd_name == "k_cd_dense" and world == 1 and args.workload == "ageing_full_377x44477_K23_fit") else None
             roof_dom = {"bound": "tensor", "kernel": cd_name, "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
                         "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": traffic,
                         "peak_source": "FP64 pipe peak measured with DMMA m8n8k4 by tools/microbench.cu on this pool's B200 (MEASURED_PEAKS.json has "

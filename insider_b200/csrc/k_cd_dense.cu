@@ -9,7 +9,9 @@
 // the warp
 //   * relabels q and beta into visiting order (thread-private transposition through shared memory), so that step i of the
 //     fully unrolled sweep touches registers q[i], b[i]: no dynamic register index, no dispatch, one basic block per sweep;
-//   * reads row i of a copy of XtX permuted into the same order (built for the NEXT sweep while this one runs).
+//   * reads row i of a copy of XtX permuted into the same order, which arrives for the NEXT sweep while this one runs:
+//     fetched with one TMA bulk copy from the pre-permuted set of all 4096 orders (iterations with many sweeps), or built
+//     in place from the coordinate-order table (steady state: a few sweeps per gene do not pay for 22 MB of tables).
 // What bounds it (ncu, profiles/r01_ncu_k_cd_dense_*.txt): every step needs the 24 doubles of the table row in every
 // thread, and a broadcast LDS costs one shared-memory wavefront per double: the shared-memory data pipe runs at 85 % of its
 // peak with the FP64 pipe at 35-38 %. Measured alternatives: XtX through the constant bank (ptxas emits LDCU.128 into two
@@ -36,6 +38,7 @@ struct CdDenseArgs {
     const double* XtX;               // K x K, element (r, c) at r*xs_r + c*xs_c
     int xs_r, xs_c;
     const double* table;             // [KT][KT + 4] prepared by k_cd_table (row r: XtX[r][:], XtX_rr, 1/(XtX_rr + l2), 0, 0)
+    const double* tables_all;        // optional [PERM_T][KT][KT + 4]: the table permuted into every visiting order (k_cd_tables_all)
     const double* Xty; const double* W0; double* Vout;     // per gene, stride ldv (Vout may alias W0)
     int64_t ldv;
     int K; int64_t P;
@@ -117,6 +120,31 @@ __device__ __forceinline__ void cd_sweep(std::integer_sequence<int, Is...>, doub
                                          const uint32_t (&ow)[KT / 4], int srcA, int lane) {
     ((cd_step<KT, Is>(q, b, Xp, incp, la, l2, dl), build_row<KT, Is>(Xn, Xs, ow, srcA, lane)), ...);
 }
+// the same without the table build: the next table arrives by a TMA bulk copy from the pre-permuted set (no LSU wavefronts)
+template <int KT, int... Is>
+__device__ __forceinline__ void cd_sweep_nobuild(std::integer_sequence<int, Is...>, double (&q)[KT], double (&b)[KT], const double* __restrict__ Xp,
+                                                 uint32_t incp, double la, double l2, double& dl) {
+    (cd_step<KT, Is>(q, b, Xp, incp, la, l2, dl), ...);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// tables_all[t] = the prepared table permuted into visiting order t of the K coordinates (order table of common.cuh):
+// out[t][i][l] = table[k_i][k_l] for l < KT (positions >= K: identity), out[t][i][KT..KT+3] = table[k_i][KT..KT+3]
+__global__ void __launch_bounds__(128) k_cd_tables_all(const double* __restrict__ table, const unsigned char* __restrict__ perm_table, int K, int KT,
+                                                       double* __restrict__ out) {
+    __shared__ unsigned char ord[32];
+    const int XLD = KT + 4, t = blockIdx.x;
+    if (threadIdx.x < 32) ord[threadIdx.x] = perm_table[PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + t) * 32 + threadIdx.x];
+    __syncthreads();
+    double* o = out + (size_t)t * KT * XLD;
+    for (int x = threadIdx.x; x < KT * XLD; x += blockDim.x) {
+        const int i = x / XLD, l = x % XLD;
+        const int ki = (i < K) ? ord[i] : i;
+        const int kl = (l < KT) ? ((l < K) ? ord[l] : l) : l;
+        o[x] = table[ki * XLD + kl];
+    }
+}
+
 
 // The XtX table in coordinate order, ready to be copied into shared memory by every block: row r = XtX[r][0..KT) (zero padded),
 // XtX_rr, 1/(XtX_rr + l2), 0, 0. One small launch per column update instead of 21 dependent global loads per thread in each of
@@ -140,7 +168,7 @@ __global__ void __launch_bounds__(256) k_cd_table(const double* __restrict__ XtX
 // the latency of their longest genes, and of the small shards of a multi-GPU run. MINB = 10 (200 registers): all 1390 blocks
 // of the 44 477-gene problem are resident at once; at steady state (4 sweeps per gene) a second wave of blocks costs more
 // than the slower sweep. lib.cu switches after the first iterations.
-template <int KT>
+template <int KT, bool TMA>
 __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
     constexpr int XLD = KT + 4;
     constexpr int NW = KT / 4;                         // 32-bit words holding KT position bytes
@@ -149,15 +177,17 @@ __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double* Xs = reinterpret_cast<double*>(smem_raw);                        // block: XtX table in coordinate order
     double* Xw = Xs + KT * XLD + warp * 2 * WBUF;                            // warp: two buffers (current / next sweep)
-    unsigned char* bytes = reinterpret_cast<unsigned char*>(Xs + KT * XLD + DW * 2 * WBUF) + warp * 128;
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(Xs + KT * XLD + DW * 2 * WBUF) + warp * 144;
     unsigned char* ord_s = bytes;                                            // [2][32] visiting order of the current / next sweep
     unsigned char* rank_s = bytes + 64;                                      // [32] rank of every coordinate in the next order
     unsigned char* np_s = bytes + 96;                                        // [32] next position of the value at current position j
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bytes + 128);               // [2] arrival of the two table buffers (TMA)
     const int K = a.K;
     const double la = a.la, l2 = a.l2;
     const double tol = a.tol_dev ? *a.tol_dev : a.tol_host;
     const uint32_t als_iter = a.als_iter_dev ? *a.als_iter_dev : a.als_iter_host;
     const uint64_t key_iter = mix64(a.seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter));   // perm_key(): first factor
+    constexpr bool use_tma = TMA;                                             // (launch() picks TMA only with tables_all and perm_mode 1)
 
     const int64_t n_slots = a.n_slots_dev ? (int64_t)*a.n_slots_dev : a.P;
     if ((int64_t)blockIdx.x * (DW * 32) >= n_slots) return;                  // a later phase usually has far fewer genes than blocks
@@ -175,6 +205,7 @@ __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
         }
     }
     ord_s[lane] = (unsigned char)lane;                                       // order before the first sweep: identity (positions = coordinates)
+    if (use_tma && lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
 
     // ---- this thread's gene; positions = coordinates until the first sweep relabels them
@@ -274,18 +305,32 @@ __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
         const int srcA = (lane < K) ? (int)ord_s[32 * cur + lane] : lane;
         build_table<KT>(std::make_integer_sequence<int, KT>{}, Xw + cur * WBUF, Xs, ow, srcA, lane);
     }
+    uint32_t tma_count[2] = {0u, 0u};                                        // fetches issued into each buffer (mbarrier phase parity)
     while (true) {
         // order of the next sweep (prefetched words) and the relabelling into it; then its table is built during this sweep
         publish_next(row_w, cur ^ 1, cur);                                   // (its __syncwarp also orders the table build / relabel of the last sweep)
         row_w = row_word(draw + 2);                                          // consumed by the sweep after the next one
         const double* Xp = Xw + cur * WBUF;
         double* Xn = Xw + (cur ^ 1) * WBUF;
-        uint32_t ow[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s + 32 * (cur ^ 1))[w];
-        const int srcA = (lane < K) ? (int)ord_s[32 * (cur ^ 1) + lane] : lane;
         double dl = 0.0;
-        cd_sweep<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, l2, dl, Xn, Xs, ow, srcA, lane);
+        if constexpr (use_tma) {
+            // the next sweep's table comes from the pre-permuted set: one bulk copy, issued now, awaited after this sweep. The
+            // buffer was the relabel scratch of the last sweep (generic-proxy accesses, ordered by the __syncwarp above).
+            if (lane == 0) {
+                const uint64_t pk = key_iter ^ mix64((uint64_t)(draw + 1) * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+                fence_proxy_async_smem();
+                mbar_expect_tx(&bars[cur ^ 1], (uint32_t)(KT * XLD * 8));
+                tma_load_1d(Xn, a.tables_all + (size_t)perm_select(pk) * (KT * XLD), (uint32_t)(KT * XLD * 8), &bars[cur ^ 1]);
+            }
+            ++tma_count[cur ^ 1];
+            cd_sweep_nobuild<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, l2, dl);
+        } else {
+            uint32_t ow[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s + 32 * (cur ^ 1))[w];
+            const int srcA = (lane < K) ? (int)ord_s[32 * (cur ^ 1) + lane] : lane;
+            cd_sweep<KT>(std::make_integer_sequence<int, KT>{}, q, b, Xp, incp, la, l2, dl, Xn, Xs, ow, srcA, lane);
+        }
         // ---- end of the sweep for this gene: inner do-while test (:114), KKT re-admission (:118-124)
         if (active) {
             ++sweeps;
@@ -326,7 +371,10 @@ __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
         __syncwarp();                                                        // every lane is done reading this sweep's table
         relabel(Xw + cur * WBUF);                                            // ... which now serves as the relabel scratch
         ++draw; cur ^= 1;
+        if (use_tma) mbar_wait(&bars[cur], (tma_count[cur] - 1u) & 1u);     // the table of the sweep about to run has landed
     }
+    // (a fetch may still be in flight when the warp leaves the loop: wait for it before the block's shared memory is released)
+    if (use_tma && tma_count[cur ^ 1] > 0u) mbar_wait(&bars[cur ^ 1], (tma_count[cur ^ 1] - 1u) & 1u);
     // one atomic per warp for the statistics
     unsigned long long sw = (slot < n_slots) ? (unsigned long long)(sweeps - (int)a.draw0) : 0ull;
 #pragma unroll
@@ -337,9 +385,9 @@ __device__ __forceinline__ void cd_dense_body(const CdDenseArgs& a) {
     }
 }
 
-template <int KT> __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) { cd_dense_body<KT>(a); }
+template <int KT, bool TMA> __global__ void __launch_bounds__(DW * 32, 8) k_cd_dense(CdDenseArgs a) { cd_dense_body<KT, TMA>(a); }
 // (__launch_bounds__(32, 10) makes ptxas stop at 168 registers; __maxnreg__ lets it use the 200 that 10 blocks per SM allow)
-template <int KT> __global__ void __maxnreg__(200) k_cd_dense_r200(CdDenseArgs a) { cd_dense_body<KT>(a); }
+template <int KT> __global__ void __maxnreg__(200) k_cd_dense_r200(CdDenseArgs a) { cd_dense_body<KT, false>(a); }
 
 // Slot order for the next launch: genes sorted by descending sweep count of the previous iteration (bucketed to ~3 %:
 // exponent + 5 mantissa bits), so that the 32 genes of a warp finish together and the longest warps start first.
@@ -429,8 +477,9 @@ void launch_kt(const CdDenseArgs& a, cudaStream_t st) {
     constexpr int XLD = KT + 4;
     constexpr int WBUF = (KT * 32 > KT * XLD) ? KT * 32 : KT * XLD;
     const int blocks = (int)((a.P + DW * 32 - 1) / (DW * 32));
-    const size_t smem = (size_t)(KT * XLD + DW * 2 * WBUF) * 8 + DW * 128;
-    auto kern = (MINB == 8) ? k_cd_dense<KT> : k_cd_dense_r200<KT>;
+    const size_t smem = (size_t)(KT * XLD + DW * 2 * WBUF) * 8 + DW * 144;
+    const bool tma = a.tables_all != nullptr && a.perm_mode == 1;
+    auto kern = (MINB == 8) ? (tma ? k_cd_dense<KT, true> : k_cd_dense<KT, false>) : k_cd_dense_r200<KT>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<blocks, DW * 32, smem, st>>>(a);
 }
@@ -461,16 +510,20 @@ size_t cd_dense_table_elems() { return (size_t)32 * 36; }
 void launch_cd_dense_table(int K, const double* XtX, int xs_r, int xs_c, double lambda, double alpha, double* table, cudaStream_t st) {
     k_cd_table<<<1, 256, 0, st>>>(XtX, xs_r, xs_c, K, (K + 3) / 4 * 4, lambda * (1.0 - alpha), table);
 }
+size_t cd_dense_tables_all_elems(int K) { const int KT = (K + 3) / 4 * 4; return (size_t)PERM_T * KT * (KT + 4); }
+void launch_cd_dense_tables_all(int K, const double* table, const unsigned char* perm_table, double* tables_all, cudaStream_t st) {
+    k_cd_tables_all<<<PERM_T, 128, 0, st>>>(table, perm_table, K, (K + 3) / 4 * 4, tables_all);
+}
 
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
                      unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, const double* table,
-                     bool resident_all, const CdPhaseState* ps, uint32_t draw0, uint32_t cap, cudaStream_t st) {
+                     bool resident_all, const CdPhaseState* ps, uint32_t draw0, uint32_t cap, const double* tables_all, cudaStream_t st) {
     CdDenseArgs a{};
     a.XtX = UtU; a.xs_r = g.KP; a.xs_c = 1;
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
     a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.perm_table = perm_table;
-    a.draw0 = draw0; a.cap = cap;
+    a.draw0 = draw0; a.cap = cap; a.tables_all = tables_all;
     if (ps) { a.state = ps->state; a.state_inc = ps->inc; a.state_dl = ps->dl; a.alive = ps->alive; a.n_slots_dev = draw0 ? ps->n_slots : nullptr; }
     launch(a, table, resident_all, st);
 }

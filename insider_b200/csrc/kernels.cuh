@@ -118,7 +118,11 @@ size_t cd_dense_table_elems();
 void launch_cd_dense_table(int K, const double* XtX, int xs_r, int xs_c, double lambda, double alpha, double* table, cudaStream_t st);
 void launch_cd_dense(const Geom& g, const double* UtU, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
                      unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, const double* table,
-                     bool resident_all, const CdPhaseState* ps, uint32_t draw0, uint32_t cap, cudaStream_t st);
+                     bool resident_all, const CdPhaseState* ps, uint32_t draw0, uint32_t cap, const double* tables_all, cudaStream_t st);
+// tables_all (optional): the prepared table permuted into each of the PERM_T visiting orders (cd_dense_tables_all_elems(K)
+// doubles, 22 MB at K = 23); with it the solver fetches every sweep's table by one TMA bulk copy instead of building it
+size_t cd_dense_tables_all_elems(int K);
+void launch_cd_dense_tables_all(int K, const double* table, const unsigned char* perm_table, double* tables_all, cudaStream_t st);
 // order[] for the next launch_cd_dense from the sweep counts of the last one (descending, bucketed)
 // (`work`: cd_order_work_ints() ints, zero-initialised once; the kernel leaves it zeroed)
 size_t cd_order_work_ints();

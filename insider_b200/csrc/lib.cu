@@ -145,6 +145,7 @@ struct insider_session {
     int* cd_order = nullptr;             // dense CD: slot -> gene, sorted by the last iteration's sweep counts
     int* cd_order_work = nullptr;
     double* cd_table = nullptr;          // dense CD: XtX table prepared once per column update
+    double* cd_tables_all = nullptr;     // dense CD: the table in every visiting order (iterations with many sweeps per gene)
     CdPhaseState cd_phase{};             // dense CD: parked genes between the phases of a column update
     int* cd_order_parked = nullptr;      // dense CD: slot order of a later phase
     uint32_t cd_phase0 = 512;            // sweeps of the first phase (doubling afterwards)
@@ -503,6 +504,9 @@ void run_iteration(insider_session* s) {
     if (dense_cd) {
         { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, sec1.side); }
         { Launch l(s, "k_cd_table"); launch_cd_dense_table(g.K, s->UtU, g.KP, 1, s->opt.lambda2, s->opt.alpha, s->cd_table, sec1.side); }
+        if (s->cd_tables_all && s->graph_variant < 2) {   // thousands to tens of sweeps per gene: 22 MB of tables once, no per-sweep build
+            Launch l(s, "k_cd_tables_all"); launch_cd_dense_tables_all(g.K, s->cd_table, s->ctx->perm_table, s->cd_tables_all, sec1.side);
+        }
     }
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
     sec1.join();
@@ -520,13 +524,13 @@ void run_iteration(insider_session* s) {
             if (ph > 0) { Launch l(s, "k_cd_order"); launch_cd_order_parked(s->cd_phase, g.P, s->cd_order_parked, s->cd_order_work, &s->state->tol, st); }
             Launch l(s, "k_cd_dense");
             launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, ph ? s->cd_order_parked : s->cd_order,
-                            s->ctx->perm_table, s->cd_table, false, &s->cd_phase, draw0, last ? 0xffffffffu : cap, st);
+                            s->ctx->perm_table, s->cd_table, false, &s->cd_phase, draw0, last ? 0xffffffffu : cap, s->cd_tables_all, st);
             draw0 = cap; cap += std::max<uint32_t>(1u, cap / 2);                       // 512, 768, 1152, ... x1.5
         }
     } else if (dense_cd) {
         Launch l(s, "k_cd_dense");
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
-                        s->graph_variant == 2, nullptr, 0u, 0xffffffffu, st);
+                        s->graph_variant == 2, nullptr, 0u, 0xffffffffu, s->graph_variant < 2 ? s->cd_tables_all : nullptr, st);
     } else {
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
@@ -624,6 +628,8 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
         s->cd_order = s->pool.get<int>((size_t)std::max<int64_t>(1, g.P), true, st);
         s->cd_order_work = s->pool.get<int>(cd_order_work_ints(), true, st);
         s->cd_table = s->pool.get<double>(cd_dense_table_elems(), true, st);
+        if (!s->masked && s->opt.alpha != 0.0 && s->opt.perm_mode == INSIDER_PERM_COUNTER && !getenv("INSIDER_B200_CD_NO_TMA"))
+            s->cd_tables_all = s->pool.get<double>(cd_dense_tables_all_elems(g.K), false, st);
         {
             const size_t Pn = (size_t)std::max<int64_t>(1, g.P);
             s->cd_phase.state = s->pool.get<double>(Pn * 2 * (size_t)round_up(g.K, 4), false, st);

@@ -78,6 +78,47 @@ __device__ double chol_subst_stored(const double* Lf, int KP, int K, int lane, d
     return b;
 }
 
+// The same substitution with the factor in registers (lane = row: its row for the forward pass, its column of L for the
+// backward pass): per step one multiply, one shuffle, one FMA instead of two dependent shared-memory loads around them.
+// Operation for operation identical to chol_subst_stored.
+template <int KP>
+__device__ __forceinline__ double chol_subst_regs(const double* __restrict__ Lf, int K, int lane, double b) {
+    double Lrow[KP], Lcol[KP];
+    const int lr = (lane < KP) ? lane : 0;
+#pragma unroll
+    for (int i = 0; i < KP; i += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(Lf + lr * KP + i);
+        Lrow[i] = v.x; Lrow[i + 1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i < KP; ++i) Lcol[i] = Lf[i * KP + lr];
+    const double inv = Lf[KP * KP + lr];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+        if (i < K) {
+            const double xi = __shfl_sync(FULL, b * inv, i);
+            if (lane == i) b = xi;
+            else if (lane > i && lane < K) b = fma(-Lrow[i], xi, b);
+        }
+    }
+#pragma unroll
+    for (int i = KP - 1; i >= 0; --i) {
+        if (i < K) {
+            const double xi = __shfl_sync(FULL, b * inv, i);
+            if (lane == i) b = xi;
+            else if (lane < i) b = fma(-Lcol[i], xi, b);
+        }
+    }
+    return b;
+}
+// asynchronous global -> shared copy of n doubles (n even, 16-byte aligned both sides) by one warp; gs_async_wait() before use
+__device__ __forceinline__ void gs_async_copy(double* dst, const double* src, int n, int lane) {
+    for (int x = 2 * lane; x < n; x += 64)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst + x)), "l"(src + x) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void gs_async_wait() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // masked path: GLp[level][chunk][e] = sum over the chunk's rows of (G[e] - D[row][e]); grid (total levels, max chunks)
 __global__ void __launch_bounds__(256) k_level_gram(const LevelTable* __restrict__ tab, const double* __restrict__ G, const double* __restrict__ D,
                                                     double* __restrict__ GLp, int KK, int max_chunks) {
@@ -277,11 +318,54 @@ struct DenseGsArgs {
     const double* G;             // [KP*KP]
     const double* Lfac;          // [total_levels][KP*KP + KP]
     int a_in_smem;               // 1: the categorical factors fit in shared memory next to the per-warp factor buffers
+    int n_lbuf;                  // factor buffers per warp (2: the next confounder's factor is staged ahead)
+    int csr_in_smem;             // 1: co_row / co_cnt staged in shared memory
 };
 constexpr int GS_CLUSTER = 8;       // CTAs per cluster (portable maximum)
 constexpr int GS_WARPS = 16;        // warps per CTA -> 128 levels in flight
+
+// one level: w = sum over co-occurring levels of count * a_{c',s'} (+ Sx W), rhs = SB - G w, substitution with the staged factor
+template <int KPT>
+__device__ __forceinline__ double gs_level_solve(const DenseGsArgs& a, int lv, const double* As, bool a_in_smem, const double* Gs, const double* Lw, int lane,
+                                                 const int* co_row, const double* co_cnt, int e0, int e1, double sb) {
+    const int KP = a.KP, K = a.K;
+    double w = 0.0;
+    for (int eb = e0; eb < e1; eb += 32) {                                     // 32 CSR entries per batch, broadcast by shuffle
+        const int n = min(32, e1 - eb);
+        const int myrow = (lane < n) ? co_row[eb + lane] : 0;
+        const double mycnt = (lane < n) ? co_cnt[eb + lane] : 0.0;
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            const int r0 = __shfl_sync(FULL, myrow, j), r1 = __shfl_sync(FULL, myrow, j + 1), r2 = __shfl_sync(FULL, myrow, j + 2), r3 = __shfl_sync(FULL, myrow, j + 3);
+            const double c0 = __shfl_sync(FULL, mycnt, j), c1 = __shfl_sync(FULL, mycnt, j + 1), c2 = __shfl_sync(FULL, mycnt, j + 2), c3 = __shfl_sync(FULL, mycnt, j + 3);
+            double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (lane < KP) {
+                if (a_in_smem) { v0 = As[(size_t)r0 * KP + lane]; v1 = As[(size_t)r1 * KP + lane]; v2 = As[(size_t)r2 * KP + lane]; v3 = As[(size_t)r3 * KP + lane]; }
+                else { v0 = __ldcg(As + (size_t)r0 * KP + lane); v1 = __ldcg(As + (size_t)r1 * KP + lane); v2 = __ldcg(As + (size_t)r2 * KP + lane); v3 = __ldcg(As + (size_t)r3 * KP + lane); }
+            }
+            w = fma(c0, v0, w); w = fma(c1, v1, w); w = fma(c2, v2, w); w = fma(c3, v3, w);
+        }
+        for (; j < n; ++j) {
+            const int r0 = __shfl_sync(FULL, myrow, j);
+            const double c0 = __shfl_sync(FULL, mycnt, j);
+            if (lane < KP) w = fma(c0, a_in_smem ? As[(size_t)r0 * KP + lane] : __ldcg(As + (size_t)r0 * KP + lane), w);
+        }
+    }
+    if (lane < KP) for (int q = 0; q < a.Q; ++q) w = fma(a.Sx[(size_t)lv * a.Q + q], a.W[(size_t)q * KP + lane], w);
+    double acc = 0.0;
+    for (int m = 0; m < KP; ++m) {
+        const double wm = __shfl_sync(FULL, w, m);
+        if (lane < KP) acc = fma(Gs[m * KP + lane], wm, acc);
+    }
+    const double rhs = (lane < KP) ? sb - acc : 0.0;
+    __syncwarp();
+    return chol_subst_regs<KPT>(Lw, K, lane, rhs);                             // :190
+}
+
+template <int KPT>
 __global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 32, 1) k_rows_dense_gs(DenseGsArgs a) {
-    extern __shared__ double gs_smem[];                // G [KP*KP] | A copy [total_levels*KP] (if a.a_in_smem) | per-warp factor [KP*KP + KP]
+    // shared memory: G [KP*KP] | A copy [total_levels*KP] (if a.a_in_smem) | per-warp factor buffers [a.n_lbuf][KP*KP + KP]
+    extern __shared__ double gs_smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int KP = a.KP, K = a.K, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = (int)cluster.block_rank() * GS_WARPS + warp, n_gw = GS_CLUSTER * GS_WARPS;
@@ -289,63 +373,71 @@ __global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 
     const int n_lv = a.lvl_first[a.C];
     double* Gs = gs_smem;
     double* As = gs_smem + KP * KP;                                            // this CTA's copy of all categorical factors
-    double* Lw = As + (a.a_in_smem ? (size_t)n_lv * KP : 0) + (size_t)warp * FK;
+    double* Lw0 = As + (a.a_in_smem ? (size_t)n_lv * KP : 0) + (size_t)warp * a.n_lbuf * FK;
     for (int x = threadIdx.x; x < KP * KP; x += blockDim.x) Gs[x] = a.G[x];
-    const double* Asrc = a.a_in_smem ? As : a.A_all;
+    // the design's co-occurrence lists (constant), staged once when they fit: a level of a small confounder co-occurs with every
+    // level of the others (131 entries for the 2-level one), and every 32-entry batch read from global memory is an L2 round trip
+    const int nnz = a.co_ptr[n_lv];
+    const double* co_cnt = a.co_cnt; const int* co_row = a.co_row;
+    if (a.csr_in_smem) {
+        double* cnt_s = Lw0 - (size_t)warp * a.n_lbuf * FK + (size_t)GS_WARPS * a.n_lbuf * FK;      // after all factor buffers
+        int* row_s = reinterpret_cast<int*>(cnt_s + nnz);
+        for (int x = threadIdx.x; x < nnz; x += blockDim.x) { cnt_s[x] = a.co_cnt[x]; row_s[x] = a.co_row[x]; }
+        co_cnt = cnt_s; co_row = row_s;
+    }
+    // Fast path (a.a_in_smem && a.n_lbuf == 2): every CTA keeps all factors in shared memory; a solved level is written into
+    // the copies of all 8 CTAs through distributed shared memory, so after the cluster barrier nothing has to be re-read from
+    // global memory, and the Cholesky factor of a warp's level of the NEXT confounder is staged while this one is solved.
+    const bool fast = a.a_in_smem && a.n_lbuf == 2;
+    if (a.a_in_smem) {
+        int x = threadIdx.x; const int nthr = blockDim.x, n = n_lv * KP;
+        for (; x + 3 * nthr < n; x += 4 * nthr) {
+            const double v0 = __ldcg(a.A_all + x), v1 = __ldcg(a.A_all + x + nthr), v2 = __ldcg(a.A_all + x + 2 * nthr), v3 = __ldcg(a.A_all + x + 3 * nthr);
+            As[x] = v0; As[x + nthr] = v1; As[x + 2 * nthr] = v2; As[x + 3 * nthr] = v3;
+        }
+        for (; x < n; x += nthr) As[x] = __ldcg(a.A_all + x);
+    }
+    // scalars of this warp's first level of the next confounder, fetched one confounder ahead (global loads off the chain)
+    int pe0 = 0, pe1 = 0; double psb = 0.0;
+    auto prefetch_level = [&](int c) {
+        const int lvn = a.lvl_first[c] + gw;
+        if (lvn < a.lvl_first[c + 1]) {
+            pe0 = a.co_ptr[lvn]; pe1 = a.co_ptr[lvn + 1];
+            psb = (lane < KP) ? a.SB[(size_t)lvn * KP + lane] : 0.0;
+            if (fast) gs_async_copy(Lw0 + (size_t)(c & 1) * FK, a.Lfac + (size_t)lvn * FK, FK, lane);
+        }
+    };
+    if (a.C > 0) prefetch_level(0);
+    cluster.sync();                                                            // every CTA's copy is complete before remote writes start
     for (int c = 0; c < a.C; ++c) {                                            // src/optimize.cpp:335 (fixed block order)
-        // (re)load the factors: blocks updated earlier in this sweep were written by other CTAs of the cluster
-        if (a.a_in_smem) {
-            // __ldcg semantics are not needed for correctness of plain loads here: the data was written before a cluster.sync
-            // (release/acquire at cluster scope) and As is refilled after it; L1 holds no stale copy because A_all is only
-            // ever read through this staging copy.
+        if (!fast && a.a_in_smem && c > 0) {
+            // slow path: re-read the factors (blocks updated earlier in this sweep were written by other CTAs of the cluster)
             int x = threadIdx.x; const int nthr = blockDim.x, n = n_lv * KP;
-            for (; x + 3 * nthr < n; x += 4 * nthr) {
-                const double v0 = __ldcg(a.A_all + x), v1 = __ldcg(a.A_all + x + nthr), v2 = __ldcg(a.A_all + x + 2 * nthr), v3 = __ldcg(a.A_all + x + 3 * nthr);
-                As[x] = v0; As[x + nthr] = v1; As[x + 2 * nthr] = v2; As[x + 3 * nthr] = v3;
-            }
             for (; x < n; x += nthr) As[x] = __ldcg(a.A_all + x);
+            __syncthreads();
         }
-        __syncthreads();
-        for (int lv = a.lvl_first[c] + gw; lv < a.lvl_first[c + 1]; lv += n_gw) {
-            // stage this level's Cholesky factor (independent loads, issued before anything depends on them)
-            const double* Lf = a.Lfac + (size_t)lv * FK;
-            copy_batched(Lw, Lf, FK, lane, 32);
-            // w = sum over co-occurring levels of count * a_{c',s'}: 32 CSR entries per batch, broadcast by shuffle
-            double w = 0.0;
-            const int e0 = a.co_ptr[lv], e1 = a.co_ptr[lv + 1];
-            for (int eb = e0; eb < e1; eb += 32) {
-                const int n = min(32, e1 - eb);
-                const int myrow = (lane < n) ? a.co_row[eb + lane] : 0;
-                const double mycnt = (lane < n) ? a.co_cnt[eb + lane] : 0.0;
-                int j = 0;
-                for (; j + 3 < n; j += 4) {
-                    const int r0 = __shfl_sync(FULL, myrow, j), r1 = __shfl_sync(FULL, myrow, j + 1), r2 = __shfl_sync(FULL, myrow, j + 2), r3 = __shfl_sync(FULL, myrow, j + 3);
-                    const double c0 = __shfl_sync(FULL, mycnt, j), c1 = __shfl_sync(FULL, mycnt, j + 1), c2 = __shfl_sync(FULL, mycnt, j + 2), c3 = __shfl_sync(FULL, mycnt, j + 3);
-                    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                    if (lane < KP) {
-                        if (a.a_in_smem) { v0 = As[(size_t)r0 * KP + lane]; v1 = As[(size_t)r1 * KP + lane]; v2 = As[(size_t)r2 * KP + lane]; v3 = As[(size_t)r3 * KP + lane]; }
-                        else { v0 = __ldcg(Asrc + (size_t)r0 * KP + lane); v1 = __ldcg(Asrc + (size_t)r1 * KP + lane); v2 = __ldcg(Asrc + (size_t)r2 * KP + lane); v3 = __ldcg(Asrc + (size_t)r3 * KP + lane); }
-                    }
-                    w = fma(c0, v0, w); w = fma(c1, v1, w); w = fma(c2, v2, w); w = fma(c3, v3, w);
-                }
-                for (; j < n; ++j) {
-                    const int r0 = __shfl_sync(FULL, myrow, j);
-                    const double c0 = __shfl_sync(FULL, mycnt, j);
-                    if (lane < KP) w = fma(c0, a.a_in_smem ? As[(size_t)r0 * KP + lane] : __ldcg(Asrc + (size_t)r0 * KP + lane), w);
+        const double* Asrc = a.a_in_smem ? As : a.A_all;
+        int it = 0;
+        for (int lv = a.lvl_first[c] + gw; lv < a.lvl_first[c + 1]; lv += n_gw, ++it) {
+            double* Lw = Lw0 + (size_t)((fast && it == 0) ? (c & 1) : 0) * FK;
+            int e0, e1; double sb;
+            if (it == 0) { e0 = pe0; e1 = pe1; sb = psb; }
+            else { e0 = a.co_ptr[lv]; e1 = a.co_ptr[lv + 1]; sb = (lane < KP) ? a.SB[(size_t)lv * KP + lane] : 0.0; }
+            if (fast && it == 0) { gs_async_wait(); }                          // staged ahead (asynchronous copy)
+            else { __syncwarp(); copy_batched(Lw, a.Lfac + (size_t)lv * FK, FK, lane, 32); }
+            __syncwarp();
+            if (it == 0 && c + 1 < a.C) prefetch_level(c + 1);                 // next confounder's level: factor + scalars
+            const double x = gs_level_solve<KPT>(a, lv, Asrc, a.a_in_smem != 0, Gs, Lw, lane, co_row, co_cnt, e0, e1, sb);
+            if (lane < K) {
+                a.A_all[(size_t)lv * KP + lane] = x;
+                if (fast) {
+#pragma unroll
+                    for (int r = 0; r < GS_CLUSTER; ++r) cluster.map_shared_rank(As, r)[(size_t)lv * KP + lane] = x;
                 }
             }
-            if (lane < KP) for (int q = 0; q < a.Q; ++q) w = fma(a.Sx[(size_t)lv * a.Q + q], a.W[(size_t)q * KP + lane], w);
-            double acc = 0.0;
-            for (int m = 0; m < KP; ++m) {
-                const double wm = __shfl_sync(FULL, w, m);
-                if (lane < KP) acc = fma(Gs[m * KP + lane], wm, acc);
-            }
-            const double rhs = (lane < KP) ? a.SB[(size_t)lv * KP + lane] - acc : 0.0;
-            __syncwarp();
-            const double x = chol_subst_stored(Lw, KP, K, lane, rhs);         // :190
-            if (lane < K) a.A_all[(size_t)lv * KP + lane] = x;
             __syncwarp();
         }
+        if (it == 0 && c + 1 < a.C) prefetch_level(c + 1);                     // no level in this confounder: still look ahead
         __threadfence();
         cluster.sync();                                                        // block c is complete and visible cluster-wide
     }
@@ -500,15 +592,19 @@ void launch_level_sumB(const Geom& g, const LevelTable* tab_dev, int total_level
     if (total_levels) k_level_sumB<<<total_levels, 128, 0, st>>>(tab_dev, g.KP, B, SB);
 }
 
-void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, double* A_all, const double* W, const double* SB,
-                          const double* G, const double* Lfac, cudaStream_t st) {
-    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0};
+void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
+                          const double* SB, const double* G, const double* Lfac, cudaStream_t st) {
+    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0, 1, 0};
     const size_t FK = (size_t)g.KP * g.KP + g.KP, limit = 227 * 1024;
     size_t smem = ((size_t)g.KP * g.KP + GS_WARPS * FK) * 8;
     if (smem + (size_t)total_levels * g.KP * 8 <= limit) { a.a_in_smem = 1; smem += (size_t)total_levels * g.KP * 8; }
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_rows_dense_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit); attr_set = true; }
-    k_rows_dense_gs<<<GS_CLUSTER, GS_WARPS * 32, smem, st>>>(a);
+    if (smem + (size_t)nnz * 12 + 8 <= limit) { a.csr_in_smem = 1; smem += (size_t)nnz * 12 + 8; }
+    // second factor buffer (staging ahead): only when every warp has at most one level per confounder
+    if (a.a_in_smem && max_levels <= GS_CLUSTER * GS_WARPS && smem + GS_WARPS * FK * 8 <= limit) { a.n_lbuf = 2; smem += GS_WARPS * FK * 8; }
+#define GS_LAUNCH(KPv) { cudaFuncSetAttribute(k_rows_dense_gs<KPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit); \
+                         k_rows_dense_gs<KPv><<<GS_CLUSTER, GS_WARPS * 32, smem, st>>>(a); }
+    switch (g.NT) { case 1: GS_LAUNCH(8) break; case 2: GS_LAUNCH(16) break; case 3: GS_LAUNCH(24) break; default: GS_LAUNCH(32) break; }
+#undef GS_LAUNCH
 }
 
 size_t continuous_scratch_elems(const Geom& g) { return (size_t)((g.N + 63) / 64) * (g.KP * g.KP + g.KP); }

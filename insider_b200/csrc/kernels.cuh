@@ -74,7 +74,7 @@ void launch_level_update(const Geom& g, bool masked, const RowDesign& d, int lfa
 // all confounder blocks in one single-block launch using the design's co-occurrence counts (no N-length loops)
 struct DenseGs { const int* lvl_first; const int* co_ptr; const int* co_row; const double* co_cnt; const double* Sx; };
 void launch_level_sumB(const Geom& g, const LevelTable* tab_dev, int total_levels, const double* B, double* SB, cudaStream_t st);
-void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, double* A_all, const double* W, const double* SB,
+void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W, const double* SB,
                           const double* G, const double* Lfac, cudaStream_t st);
 // continuous covariate q: H = sum_k x_k^2 Gk_k, Tq = sum_k x_k (B_k - Gk_k u_k); cyclic coordinate update / solve; updates w and U
 void launch_continuous(const Geom& g, bool masked, const double* x, double* w /*[KP]*/, const double* B, const double* G, const double* D,

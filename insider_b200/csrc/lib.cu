@@ -104,6 +104,7 @@ struct insider_resident {
     // dense-path Gauss-Seidel tables (design only): co-occurrence CSR over all levels, per-level sums of X
     int total_levels = 0;
     int *gs_lvl_first = nullptr, *gs_co_ptr = nullptr, *gs_co_row = nullptr;
+    int gs_nnz = 0;
     double *gs_co_cnt = nullptr, *gs_Sx = nullptr;
     double n_train = 0, n_test = 0;
     double h2d_bytes = 0;
@@ -293,6 +294,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
                     for (auto& kv : co) { rows.push_back(kv.first); cnts.push_back((double)kv.second); }
                     ptr[first[c] + l + 1] = (int)rows.size();
                 }
+            r->gs_nnz = (int)rows.size();
             r->gs_lvl_first = r->pool.get<int>(first.size(), false);
             r->gs_co_ptr = r->pool.get<int>(ptr.size(), false);
             r->gs_co_row = r->pool.get<int>(std::max<size_t>(1, rows.size()), false);
@@ -484,7 +486,7 @@ void run_iteration(insider_session* s) {
     } else if (r->C > 0) {
         // dense path: per-level sums of B once, then all C block updates in one single-block launch on factor-sized data
         DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
-        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs(g, dg, r->C, r->Q, s->total_levels, s->A_all, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->SB, s->G, s->Lfac, st); }
+        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs(g, dg, r->C, r->Q, s->total_levels, r->L.empty() ? 0 : *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz, s->A_all, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->SB, s->G, s->Lfac, st); }
         if (r->inc_continuous) {   // the continuous block below works on the row factor: rebuild it with the new A_c
             Launch l(s, "k_build_u", 2);
             launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, s->A_all + s->a_off[r->C], s->U, s->Ut, s->UtU, st);

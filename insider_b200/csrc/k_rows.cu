@@ -93,21 +93,19 @@ __device__ __forceinline__ double chol_subst_regs(const double* __restrict__ Lf,
 #pragma unroll
     for (int i = 0; i < KP; ++i) Lcol[i] = Lf[i * KP + lr];
     const double inv = Lf[KP * KP + lr];
+    // no `i < K` guards: for the padding rows K..KP-1 the stored inverse diagonal is 0 and the right-hand side is 0, so their
+    // steps are exact no-ops - and the whole substitution is one basic block
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
-        if (i < K) {
-            const double xi = __shfl_sync(FULL, b * inv, i);
-            if (lane == i) b = xi;
-            else if (lane > i && lane < K) b = fma(-Lrow[i], xi, b);
-        }
+        const double xi = __shfl_sync(FULL, b * inv, i);
+        const double upd = fma(-Lrow[i], xi, b);
+        b = (lane == i) ? xi : ((lane > i && lane < K) ? upd : b);
     }
 #pragma unroll
     for (int i = KP - 1; i >= 0; --i) {
-        if (i < K) {
-            const double xi = __shfl_sync(FULL, b * inv, i);
-            if (lane == i) b = xi;
-            else if (lane < i) b = fma(-Lcol[i], xi, b);
-        }
+        const double xi = __shfl_sync(FULL, b * inv, i);
+        const double upd = fma(-Lcol[i], xi, b);
+        b = (lane == i) ? xi : ((lane < i) ? upd : b);
     }
     return b;
 }
@@ -353,9 +351,11 @@ __device__ __forceinline__ double gs_level_solve(const DenseGsArgs& a, int lv, c
     }
     if (lane < KP) for (int q = 0; q < a.Q; ++q) w = fma(a.Sx[(size_t)lv * a.Q + q], a.W[(size_t)q * KP + lane], w);
     double acc = 0.0;
-    for (int m = 0; m < KP; ++m) {
+    const int lg = (lane < KPT) ? lane : 0;
+#pragma unroll
+    for (int m = 0; m < KPT; ++m) {                                            // G w, same order of accumulation as before
         const double wm = __shfl_sync(FULL, w, m);
-        if (lane < KP) acc = fma(Gs[m * KP + lane], wm, acc);
+        acc = fma(Gs[m * KPT + lg], wm, acc);
     }
     const double rhs = (lane < KP) ? sb - acc : 0.0;
     __syncwarp();

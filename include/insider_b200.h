@@ -164,9 +164,9 @@ int insider_b200_als_profile(insider_session* s, char* names, size_t names_len, 
 void insider_b200_set_profile(insider_ctx* ctx, int on);
 /* diagnostics: coordinate-descent sweeps every local gene needed in the last iteration (the count strong_coordinate_descent's
  * do-while ran, src/coordinate_descent.cpp:86-114); n = number of entries of `out`, at most the context's local gene count.
- * Returns the number of entries written (0 when the last column update was a ridge solve or the masked solver). */
+ * Returns the number of entries written (0 when the column update is a ridge solve, alpha = 0). */
 int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n);
-/* optional hint for the dense elastic-net solver: expected sweep count of every local gene in the NEXT iteration (e.g. the
+/* optional hint for the elastic-net solvers: expected sweep count of every local gene in the NEXT iteration (e.g. the
  * counts of a previous fit of the same data). It only orders the work (genes with similar counts share a warp); results do
  * not depend on it. Returns the number of entries taken. */
 int64_t insider_b200_als_hint_sweeps(insider_session* s, const int32_t* hint, int64_t n);

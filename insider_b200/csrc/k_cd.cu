@@ -158,6 +158,7 @@ struct CdArgs {
     uint64_t seed; int perm_mode;
     unsigned long long* sweeps_total; unsigned long long* steps_total; int* sweeps_per_gene;
     unsigned int* queue;          // atomic gene counter (zeroed before launch)
+    const int* order;             // optional [P]: the queue hands out gene order[i] (longest expected solves first)
     const unsigned char* perm_table;   // rank + order tables (common.cuh)
 };
 
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
             if ((int64_t)jn >= a.P) {
                 retired = true;
             } else {
-                gene = (int64_t)jn;
+                gene = a.order ? (int64_t)a.order[jn] : (int64_t)jn;
                 if (PERGENE) {
                     // per-gene matrix global -> shared, eight independent loads in flight per lane (a plain strided loop
                     // pays one L2 round trip per element: 72 of them per gene)
@@ -451,7 +452,7 @@ void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const 
 
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
                       unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
-                      int sm_count, cudaStream_t st) {
+                      int sm_count, int* sweeps_per_gene, const int* order, cudaStream_t st) {
     if (g.P == 0) return;
     if (p.alpha == 0.0) {
         RidgeArgs r{UtU, XtXall, Xty, V, g.K, g.KP, g.ldV, g.P, p.lambda, err_flag};
@@ -465,7 +466,7 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
     a.Xsh = UtU; a.Xall = XtXall; a.x_stride = (int64_t)g.KP * g.KP; a.xs_r = g.KP; a.xs_c = 1;
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P; a.gene0 = g.gene0;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
-    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = nullptr; a.queue = queue; a.perm_table = perm_table;
+    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.queue = queue; a.perm_table = perm_table;
     launch_cd(a, g.KP, masked, sm_count, st);
 }
 

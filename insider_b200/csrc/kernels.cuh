@@ -96,9 +96,11 @@ struct CdParams {
 // masked path: XtXall[j][KP*KP] = UtU - sum_{i: m_ij=0} u_i u_i^T for every local gene (DMMA gathers, one warp per gene)
 void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, double* XtXall, cudaStream_t st);
 // per gene: alpha == 0 -> ridge solve, else elastic-net CD (persistent groups pulling genes from `queue`). Updates V in place.
+// sweeps_per_gene / order (optional): record every gene's sweep count; hand the genes out in the given order (launch_cd_order
+// on the previous iteration's counts: the longest solves start first, which shortens the tail of the launch).
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
                       unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
-                      int sm_count, cudaStream_t st);
+                      int sm_count, int* sweeps_per_gene, const int* order, cudaStream_t st);
 // dense path, alpha != 0: thread-per-gene elastic-net CD with the shared Gram UtU (k_cd_dense.cu). `order` (optional) maps
 // thread slots to genes; `sweeps_per_gene` (optional) receives every gene's sweep count.
 // `table`: cd_dense_table_elems() doubles filled by launch_cd_dense_table() from UtU (independent of Xty: may run beside

@@ -534,8 +534,11 @@ void run_iteration(insider_session* s) {
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
                         s->graph_variant == 2, nullptr, 0u, 0xffffffffu, s->graph_variant < 2 ? s->cd_tables_all : nullptr, st);
     } else {
+        const bool masked_cd = s->masked && s->opt.alpha != 0.0;
+        if (masked_cd) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
         Launch l(s, "k_col_solve");
-        launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count, st);
+        launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count,
+                         masked_cd ? s->sweeps_gene : nullptr, masked_cd ? s->cd_order : nullptr, st);
     }
 }
 
@@ -877,7 +880,7 @@ int insider_b200_als_profile(insider_session* s, char* names, size_t names_len, 
 }
 
 int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n) {
-    if (!s || !out || n <= 0 || s->masked || s->opt.alpha == 0.0) return 0;
+    if (!s || !out || n <= 0 || s->opt.alpha == 0.0) return 0;
     n = std::min<int64_t>(n, s->g.P);
     if (cudaSetDevice(s->ctx->device) != cudaSuccess) return 0;
     if (cudaMemcpyAsync(out, s->sweeps_gene, (size_t)n * 4, cudaMemcpyDeviceToHost, s->ctx->stream) != cudaSuccess) return 0;
@@ -886,7 +889,7 @@ int64_t insider_b200_als_sweeps(insider_session* s, int32_t* out, int64_t n) {
 }
 
 int64_t insider_b200_als_hint_sweeps(insider_session* s, const int32_t* hint, int64_t n) {
-    if (!s || !hint || n <= 0 || s->masked || s->opt.alpha == 0.0) return 0;
+    if (!s || !hint || n <= 0 || s->opt.alpha == 0.0) return 0;
     n = std::min<int64_t>(n, s->g.P);
     if (cudaSetDevice(s->ctx->device) != cudaSuccess) return 0;
     if (cudaMemcpyAsync(s->sweeps_gene, hint, (size_t)n * 4, cudaMemcpyHostToDevice, s->ctx->stream) != cudaSuccess) return 0;

@@ -233,24 +233,27 @@ def test_strong_cd_screening_and_kkt_readmission_paths(ctx):
     assert hit >= 10                                             # the re-admission path really ran
 
 
-def test_per_gene_sweep_counts_match_oracle(ctx):
-    """insider_b200_als_sweeps: the do-while count of every gene in the last iteration equals the oracle's, gene by gene
-    (and does not depend on the slot order the dense solver derives from the previous iteration's counts)."""
+@pytest.mark.parametrize("tuning", [0, 1])
+def test_per_gene_sweep_counts_match_oracle(ctx, tuning):
+    """insider_b200_als_sweeps: the do-while count of every gene in the last iteration equals the oracle's, gene by gene, on the
+    dense (thread-per-gene, phased) and the masked (8 lanes per gene) solver; results are bitwise reproducible run to run and do
+    not depend on the order the solvers derive from the previous counts or from a hint."""
     import ctypes as C
     N, P, K = 40, 300, 6
     pb = synth.ageing_like(N=N, P=P, K=K, n_donors=7, seed=4)
+    tr, te = synth.random_masks(N, P, 0.1, 6)
     F0, V0 = synth.init_factors(pb.levels, K, P, seed=5)
     iters = 4
     sink = np.zeros((iters + 2, P), dtype=np.int32)
     oracle.lib().oracle_set_sweep_sink(sink.ctypes.data_as(C.POINTER(C.c_int)), C.c_longlong(sink.size))
     try:
-        oracle.optimize(pb.Y, F0, V0, pb.confounder, None, None, None, 0, K, 3.0, 3.0, 0.4, 0, 1e-12, 1e-5, iters - 1, perm_mode=1, seed=9)
+        oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 3.0, 3.0, 0.4, tuning, 1e-12, 1e-5, iters - 1, perm_mode=1, seed=9)
     finally:
         oracle.lib().oracle_set_sweep_sink(None, C.c_longlong(0))
-    res = ctx.upload(_cabi.HostProblem(pb.Y, pb.confounder, None, None, None, 0))
+    res = ctx.upload(_cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0))
     opt = _cabi.default_options()
     opt.lambda1 = opt.lambda2 = 3.0
-    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = 0.4, 0, 1e-12, 1e-5, 10 ** 6, 9
+    opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = 0.4, tuning, 1e-12, 1e-5, 10 ** 6, 9
     runs = []
     for rep in range(2):
         fac = _cabi.HostFactors(F0, V0, K)
@@ -262,10 +265,9 @@ def test_per_gene_sweep_counts_match_oracle(ctx):
             np.testing.assert_array_equal(s.sweeps(P), sink[it])
         s.end()
         runs.append((fac.V.copy(), [f.copy() for f in fac.factors]))
-    # bitwise reproducible run to run (the slot order of the dense solver comes from atomics; results must not depend on it)
     np.testing.assert_array_equal(runs[0][0], runs[1][0])
-    for a, b in zip(runs[0][1], runs[1][1]):
-        np.testing.assert_array_equal(a, b)
+    for a_, b_ in zip(runs[0][1], runs[1][1]):
+        np.testing.assert_array_equal(a_, b_)
     res.release()
 
 

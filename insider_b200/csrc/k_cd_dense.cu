@@ -13,13 +13,20 @@
 //     fetched with one TMA bulk copy from the pre-permuted set of all 4096 orders (iterations with many sweeps), or built
 //     in place from the coordinate-order table (steady state: a few sweeps per gene do not pay for 22 MB of tables).
 // What bounds it (ncu, profiles/r01_ncu_k_cd_dense_*.txt): every step needs the 24 doubles of the table row in every
-// thread, and a broadcast LDS costs one shared-memory wavefront per double: the shared-memory data pipe runs at 85 % of its
-// peak with the FP64 pipe at 35-38 %. Measured alternatives: XtX through the constant bank (ptxas emits LDCU.128 into two
+// thread, and a broadcast LDS costs one shared-memory wavefront per double: the shared-memory data pipe runs at 92-93 % of
+// its peak with the FP64 pipe at ~40 %. Measured alternatives: XtX through the constant bank (ptxas emits LDCU.128 into two
 // uniform-register quads and serialises on them: 1.6x slower); two genes per thread sharing every row load (half the
 // wavefronts per gene, but half the warps at the same cycles-per-instruction: 1.15x slower); `switch (k)` on coordinate-
 // order registers instead of relabelling (same wavefronts, plus dispatch: 1.05x slower).
-// A warp runs until its slowest gene has converged (finished genes idle); genes can be handed out in the order of their
-// previous sweep counts (`order`) so that a warp's genes finish together. Arithmetic per coordinate (covariance form,
+// Also measured and dropped: a gene split over 4 lanes (lone-warp sweep 4.1 us against 2.45 us: the shuffle sits on the
+// dependency chain), static per-SM chunks of the ordered gene list instead of the hardware block scheduler (much slower:
+// the long genes end up on few SMs), the 8-lanes-per-gene kernel of k_cd.cu on this path (2x slower at every shard size,
+// profiles/r01_cd_dense_vs_group_shard_sizes.txt).
+// A warp runs until its slowest gene has converged (finished genes idle); genes are handed out in the order of their
+// previous sweep counts (`order`, k_cd_order) so that a warp's genes finish together. The first ALS iterations, where a few
+// genes need 100x the median number of sweeps, run in PHASES (draw0/cap/state below): a launch stops every gene at sweep
+// `cap`, parks the unconverged ones (q, beta, active set, last |loss decrement|), k_cd_order compacts and re-sorts them
+// and the next launch resumes them in full warps - bitwise the same iterates, only regrouped. Arithmetic per coordinate (covariance form,
 // exact loss decrements, correctly rounded division) is identical to k_cd.cu - see the header comment there.
 #include <algorithm>
 #include <utility>

@@ -186,14 +186,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_col_xty: grid (n_blocks). Items = (tile, slab) of the block's tile range; reduction over rows is split over warps.
+// k_col_xty: grid (n_blocks). Items = (tile, slab) of the block's tile range, streamed through one ring of stages.
+// The 8 warps form TWO GROUPS of 4 (one warp of each group per SM sub-partition) that take alternate tiles: inside a group
+// the reduction over rows is split over the 4 warps and combined through shared memory in a fixed order; the groups only
+// meet in the stage ring. While one group combines and stores its tile (no DMMA work, 3 group barriers) the other is in
+// its contraction and keeps the DMMA pipe busy - one warp with 6 independent accumulators saturates a sub-partition's
+// pipe. (With all 8 warps on the same tile the pipe idled 26 % of the kernel in that epilogue: pc sampling in
+// profiles/r01_ncu_streaming_kernels_dense.txt.)
+constexpr int XG_WARPS = NWARPS / 2;           // warps per group
+constexpr int XG_THREADS = XG_WARPS * 32;
+
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "r"(XG_THREADS) : "memory"); }
+
 template <int NT, bool MASKED, bool RESIDENT_U>
 __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int grp = warp / XG_WARPS, gw = warp % XG_WARPS, gtid = tid % XG_THREADS;
     int t0, t1;
     split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
-    const int n_items = (t1 - t0) * a.n_slabs;
+    const int n_tiles_blk = t1 - t0;
+    const int n_items = n_tiles_blk * a.n_slabs;
     const int S = a.n_stages;
 
     const int ysz = TG * a.pitchS;
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     const int stage_doubles = ysz + (RESIDENT_U ? 0 : usz);
     double* Ures = reinterpret_cast<double*>(smem_raw);                       // resident Ut (if any)
     double* stage0 = Ures + (RESIDENT_U ? usz : 0);
-    double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [NWARPS][NT*2*64] when scratch_sep
+    double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [2][XG_WARPS][NT*2*64] when scratch_sep
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers + 1 for Ut
 
     if (tid == 0) {
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
             mbar_expect_tx(&bars[S], (uint32_t)usz * 8u);
             tma_load_1d(Ures, a.Ut, (uint32_t)usz * 8u, &bars[S]);
         }
-        for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
+        for (int i = 0; i < S && i < n_items; ++i) issue(i);                  // item i + S is issued by the group that consumed item i
     }
     if (RESIDENT_U) mbar_wait(&bars[S], 0);
 
@@ -246,64 +259,72 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
 #pragma unroll
         for (int m = 0; m < 2; ++m) acc[n][m][0] = acc[n][m][1] = 0.0;
 
-    for (int item = 0; item < n_items; ++item) {
-        const int s = item % S;
-        double* Ys = stage0 + (size_t)s * stage_doubles;
-        const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
-        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
-        const int r0 = slab * a.R;
-        const int rows_here = min(a.R, a.ldY - r0);
-        if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
-        uint32_t word = 0;
-        if (MASKED) {
-            const int c = tid >> 4, w = tid & 15;
-            if (32 * w < rows_here) word = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
-        }
-        mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
-        if (MASKED) {
-            premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
-            __syncthreads();
-        }
-        const int KS = rows_here >> 2;
-        int k0, k1;
-        split_range(KS, NWARPS, warp, k0, k1);
-        for (int ks = k0; ks < k1; ++ks) {
-            double av[NT], bv[2];
+    for (int tl = grp; tl < n_tiles_blk; tl += 2) {
+        const int tile = t0 + tl;
+        for (int slab = 0; slab < a.n_slabs; ++slab) {
+            const int item = tl * a.n_slabs + slab;
+            const int s = item % S;
+            double* Ys = stage0 + (size_t)s * stage_doubles;
+            const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
+            const int r0 = slab * a.R;
+            const int rows_here = min(a.R, a.ldY - r0);
+            uint32_t word[2] = {0, 0};
+            if (MASKED) {
+                const int w = gtid & 15;
 #pragma unroll
-            for (int n = 0; n < NT; ++n) av[n] = Us[(8 * n + g) * a.pitchU + 4 * ks + t];
-#pragma unroll
-            for (int m = 0; m < 2; ++m) bv[m] = Ys[(8 * m + g) * a.pitchS + 4 * ks + t];
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int m = 0; m < 2; ++m) dmma(acc[n][m][0], acc[n][m][1], av[n], bv[m]);
-        }
-        if (slab == a.n_slabs - 1) {
-            // cross-warp reduction in a fixed order, then store the K x 16 tile of Xty. The scratch
-            // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer when that is large enough.
-            double* scratch = a.scratch_sep ? scratch_own : Ys;
-            __syncthreads();
-            double* sc = scratch + warp * (NT * 2 * 64);
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[n][m][0];
-                    sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[n][m][1];
-                    acc[n][m][0] = acc[n][m][1] = 0.0;
+                for (int h = 0; h < 2; ++h) {
+                    const int c = (gtid >> 4) + 8 * h;
+                    if (32 * w < rows_here) word[h] = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
                 }
-            __syncthreads();
-            for (int x = tid; x < NT * 2 * 64; x += THREADS) {
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
-                const int tl = x >> 6, ln = (x & 63) >> 1, e = x & 1;
-                const int n = tl >> 1, m = tl & 1;
-                const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
-                if (k < a.ldV) a.out[((int64_t)tile * TG + gene) * a.ldV + k] = sum;
             }
+            mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
+            if (MASKED) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) premask(Ys, a.pitchS, word[h], gtid & 15, (gtid >> 4) + 8 * h, rows_here);
+                group_bar(grp);
+            }
+            const int KS = rows_here >> 2;
+            int k0, k1;
+            split_range(KS, XG_WARPS, gw, k0, k1);
+            for (int ks = k0; ks < k1; ++ks) {
+                double av[NT], bv[2];
+#pragma unroll
+                for (int n = 0; n < NT; ++n) av[n] = Us[(8 * n + g) * a.pitchU + 4 * ks + t];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) bv[m] = Ys[(8 * m + g) * a.pitchS + 4 * ks + t];
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) dmma(acc[n][m][0], acc[n][m][1], av[n], bv[m]);
+            }
+            if (slab == a.n_slabs - 1) {
+                // cross-warp reduction of the group in a fixed order, then store the K x 16 tile of Xty. The scratch
+                // [XG_WARPS][NT*2*64] aliases this item's (fully consumed) stage buffer when that is large enough.
+                double* scratch = a.scratch_sep ? scratch_own + (size_t)grp * XG_WARPS * (NT * 2 * 64) : Ys;
+                group_bar(grp);
+                double* sc = scratch + gw * (NT * 2 * 64);
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[n][m][0];
+                        sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[n][m][1];
+                        acc[n][m][0] = acc[n][m][1] = 0.0;
+                    }
+                group_bar(grp);
+                for (int x = gtid; x < NT * 2 * 64; x += XG_THREADS) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < XG_WARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
+                    const int tl2 = x >> 6, ln = (x & 63) >> 1, e = x & 1;
+                    const int n = tl2 >> 1, m = tl2 & 1;
+                    const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
+                    if (k < a.ldV) a.out[((int64_t)tile * TG + gene) * a.ldV + k] = sum;
+                }
+            }
+            group_bar(grp);                                                    // the group is done with stage s: refill it
+            if (gtid == 0 && item + S < n_items) { fence_proxy_async(); issue(item + S); }
         }
-        __syncthreads();
     }
 }
 

@@ -18,6 +18,7 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int NWARPS = 8;
+static_assert(NWARPS == 2 * (TG / 4), "k_row_b: two warps per k-step share the V V^T tiles");
 constexpr int MT_PER_WARP = 6;          // 8 warps x 6 m-tiles x 8 rows = 384 rows per slab
 constexpr int SLAB_ROWS_BIG = 384;      // k_row_b multi-slab
 constexpr int SLAB_ROWS_SMALL = 128;    // k_col_xty / k_sse multi-slab
@@ -28,7 +29,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 struct StreamArgs {
     const double* Y; const uint32_t* trC; const uint32_t* teC; const double* V; const double* Ut;
     double* out;                 // Bp / Xty / partial
-    double* out2;                // k_row_b: Gp[(split*4 + warp)][KP*KP] partial V V^T (slab 0 blocks, warps 0..3)
+    double* out2;                // k_row_b: Gp[(split*4 + ks)][KP*KP] partial V V^T of k-step ks (slab 0 blocks; warps 2ks, 2ks+1)
     int N, K, KP, ldY, ldV, ldT, Wp;
     int n_tiles;                 // gene tiles in total
     int R, n_slabs, pitchS, pitchU;
@@ -55,6 +56,44 @@ __device__ __forceinline__ void premask(double* Ys, int pitchS, uint32_t word, i
         int b = __ffs(z) - 1;
         z &= z - 1;
         Ys[c * pitchS + base + b] = 0.0;
+    }
+}
+
+// upper-triangle tile pairs (n1 <= n2) of an NT x NT tile grid in row-major order: idx -> n1, n2 (compile-time recursion so
+// that register arrays are only ever indexed by constants)
+template <int NT, int IDX, int N1 = 0, bool IN_ROW = (IDX < NT - N1)>
+struct GramPair { static constexpr int n1 = GramPair<NT, IDX - (NT - N1), N1 + 1>::n1, n2 = GramPair<NT, IDX - (NT - N1), N1 + 1>::n2; };
+template <int NT, int IDX, int N1>
+struct GramPair<NT, IDX, N1, true> { static constexpr int n1 = N1, n2 = N1 + IDX; };
+
+// V V^T tiles of one k-step: tiles j (first half, warp 2 ks) or GH + j (second half, warp 2 ks + 1), selected in registers
+template <int NT, int J>
+__device__ __forceinline__ void gram_steps(double (&gacc)[(NT * (NT + 1) / 2 + 1) / 2][2], const double (&bg)[NT], int ghalf) {
+    constexpr int NP = NT * (NT + 1) / 2, GH = (NP + 1) / 2;
+    if constexpr (J < GH) {
+        constexpr int J1 = (GH + J < NP) ? GH + J : NP - 1;                 // clamped: computed, not stored
+        const double ga = ghalf ? bg[GramPair<NT, J1>::n1] : bg[GramPair<NT, J>::n1];
+        const double gb = ghalf ? bg[GramPair<NT, J1>::n2] : bg[GramPair<NT, J>::n2];
+        dmma(gacc[J][0], gacc[J][1], ga, gb);
+        gram_steps<NT, J + 1>(gacc, bg, ghalf);
+    }
+}
+template <int NT, int J>
+__device__ __forceinline__ void gram_store(const double (&gacc)[(NT * (NT + 1) / 2 + 1) / 2][2], double* Gp, int KP, int ghalf, int g, int t) {
+    constexpr int NP = NT * (NT + 1) / 2, GH = (NP + 1) / 2;
+    if constexpr (J < GH) {
+        constexpr int J1 = (GH + J < NP) ? GH + J : NP - 1;
+        if (!ghalf || GH + J < NP) {
+            const int n1 = ghalf ? GramPair<NT, J1>::n1 : GramPair<NT, J>::n1;
+            const int n2 = ghalf ? GramPair<NT, J1>::n2 : GramPair<NT, J>::n2;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ra = 8 * n1 + g, cb = 8 * n2 + 2 * t + e;
+                Gp[ra * KP + cb] = gacc[J][e];
+                Gp[cb * KP + ra] = gacc[J][e];
+            }
+        }
+        gram_store<NT, J + 1>(gacc, Gp, KP, ghalf, g, t);
     }
 }
 
@@ -107,14 +146,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
     for (int i = 0; i < MT_PER_WARP; ++i)
 #pragma unroll
         for (int n = 0; n < NT; ++n) acc[i][n][0] = acc[i][n][1] = 0.0;
-    // gram = V V^T (src/optimize.cpp:332) rides along: the V fragments of k-step ks are already in registers, warp ks
-    // (of warps 0..3, slab 0 only) also accumulates the upper-triangle tiles of sum_j v_j v_j^T
-    const bool do_gram = (slab == 0) && (warp < TG / 4) && (a.out2 != nullptr);
-    double gacc[NT][NT][2];
+    // gram = V V^T (src/optimize.cpp:332) rides along (slab 0 only): k-step ks of a tile contributes 4 genes to each of the
+    // NP upper-triangle tiles of sum_j v_j v_j^T; warps 2 ks and 2 ks + 1 take half of those tiles each. The DMMAs are issued
+    // UNCONDITIONALLY with register-selected operands: a predicated-off DMMA still occupies the pipe (measured: with the gram
+    // tiles under `if (ks == warp)` every warp paid for all 24 of them, +33 % DMMA time).
+    constexpr int NP = NT * (NT + 1) / 2, GH = (NP + 1) / 2;
+    const bool do_gram = (slab == 0) && (a.out2 != nullptr);
+    const int gks = warp >> 1, ghalf = warp & 1;
+    double gacc[GH][2];
 #pragma unroll
-    for (int i = 0; i < NT; ++i)
-#pragma unroll
-        for (int n = 0; n < NT; ++n) gacc[i][n][0] = gacc[i][n][1] = 0.0;
+    for (int j = 0; j < GH; ++j) gacc[j][0] = gacc[j][1] = 0.0;
 
     for (int item = 0; item < n_items; ++item) {
         const int s = item % S;
@@ -131,17 +172,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
             premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
             __syncthreads();
         }
+        if (do_gram) {
+            double bg[NT];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) bg[n] = Vs[(4 * gks + t) * a.ldV + 8 * n + g];
+            gram_steps<NT, 0>(gacc, bg, ghalf);
+        }
 #pragma unroll
         for (int ks = 0; ks < TG / 4; ++ks) {
             double b[NT];
 #pragma unroll
             for (int n = 0; n < NT; ++n) b[n] = Vs[(4 * ks + t) * a.ldV + 8 * n + g];
-            if (do_gram && ks == warp) {
-#pragma unroll
-                for (int n1 = 0; n1 < NT; ++n1)
-#pragma unroll
-                    for (int n2 = n1; n2 < NT; ++n2) dmma(gacc[n1][n2][0], gacc[n1][n2][1], b[n1], b[n2]);
-            }
             const double* yrow = Ys + (4 * ks + t) * a.pitchS + g;
 #pragma unroll
             for (int i = 0; i < MT_PER_WARP; ++i) {
@@ -156,17 +197,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
         __syncthreads();   // stage s may be refilled
     }
     if (do_gram) {
-        double* Gp = a.out2 + ((size_t)blockIdx.x * (TG / 4) + warp) * a.KP * a.KP;
-#pragma unroll
-        for (int n1 = 0; n1 < NT; ++n1)
-#pragma unroll
-            for (int n2 = n1; n2 < NT; ++n2)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ra = 8 * n1 + g, cb = 8 * n2 + 2 * t + e;
-                    Gp[ra * a.KP + cb] = gacc[n1][n2][e];
-                    Gp[cb * a.KP + ra] = gacc[n1][n2][e];
-                }
+        double* Gp = a.out2 + ((size_t)blockIdx.x * (TG / 4) + gks) * a.KP * a.KP;
+        gram_store<NT, 0>(gacc, Gp, a.KP, ghalf, g, t);
     }
     // store the block's partial: Bp[split][N][KP]
     double* Bp = a.out + (size_t)blockIdx.x * a.N * a.KP;

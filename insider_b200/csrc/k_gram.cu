@@ -101,14 +101,19 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceJobs jobs) {
     double s = 0.0;
     if (i < n) {
         const double* p = jobs.parts[j] + i;
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        // eight independent loads in flight per thread (the V V^T job has ~600 partials on few blocks: its chain of L2 round
+        // trips is the length of this kernel)
+        double sa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int q = w;
-        for (; q + 24 < np; q += 32) {
-            const double v0 = p[(size_t)q * n], v1 = p[(size_t)(q + 8) * n], v2 = p[(size_t)(q + 16) * n], v3 = p[(size_t)(q + 24) * n];
-            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        for (; q + 56 < np; q += 64) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(q + 8 * u) * n];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sa[u] += v[u];
         }
-        for (; q < np; q += 8) s0 += p[(size_t)q * n];
-        s = (s0 + s1) + (s2 + s3);
+        for (; q < np; q += 8) sa[0] += p[(size_t)q * n];
+        s = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
     }
     sm[w][lane] = s;
     __syncthreads();

@@ -218,13 +218,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_col_xty: grid (n_blocks). Items = (tile, slab) of the block's tile range, streamed through one ring of stages.
-// The 8 warps form TWO GROUPS of 4 (one warp of each group per SM sub-partition) that take alternate tiles: inside a group
+// k_col_xty: grid (n_blocks), single-slab geometry (N <= 384 rows; launch_col_xty sends the rest to k_col_xty_slabs). Items =
+// the block's gene tiles, streamed through one ring of stages. The 8 warps form TWO GROUPS of 4 (one warp of each group per SM sub-partition) that take alternate tiles: inside a group
 // the reduction over rows is split over the 4 warps and combined through shared memory in a fixed order; the groups only
 // meet in the stage ring. While one group combines and stores its tile (no DMMA work, 3 group barriers) the other is in
 // its contraction and keeps the DMMA pipe busy - one warp with 6 independent accumulators saturates a sub-partition's
 // pipe. (With all 8 warps on the same tile the pipe idled 26 % of the kernel in that epilogue: pc sampling in
-// profiles/r01_ncu_streaming_kernels_dense.txt.)
+// profiles/r01_ncu_streaming_kernels_dense_v2.txt.)
+// Stage hand-over: item i + S is issued into item i's stage by the group that consumed item i. An mbarrier parity wait can
+// only tell the current phase from the one before it, and the two groups are not ordered against each other, so a group
+// first waits (issued[]) until ITS item has been issued into the stage and only then for the stage's phase.
 constexpr int XG_WARPS = NWARPS / 2;           // warps per group
 constexpr int XG_THREADS = XG_WARPS * 32;
 
@@ -248,9 +251,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     double* stage0 = Ures + (RESIDENT_U ? usz : 0);
     double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [2][XG_WARPS][NT*2*64] when scratch_sep
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers + 1 for Ut
+    volatile int* issued = reinterpret_cast<volatile int*>(bars + 5);         // [4] last item issued into each stage (S <= 4; 8 words reserved)
 
     if (tid == 0) {
         for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < 4; ++s) issued[s] = -1;
         mbar_fence_init();
     }
     __syncthreads();
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
             double* Us = Ys + ysz;
             for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, ybytes, &bars[s]);
         }
+        issued[s] = item;
     };
     if (tid == 0) {
         if (RESIDENT_U) {
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
         }
         for (int i = 0; i < S && i < n_items; ++i) issue(i);                  // item i + S is issued by the group that consumed item i
     }
+    __syncthreads();                                                          // issued[] of the first S items is visible to both groups
     if (RESIDENT_U) mbar_wait(&bars[S], 0);
 
     double acc[NT][2][2];
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
                     if (32 * w < rows_here) word[h] = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
                 }
             }
+            while (issued[s] < item) { }                                       // see "stage hand-over" above
             mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
             if (MASKED) {
 #pragma unroll
@@ -357,6 +365,128 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
             group_bar(grp);                                                    // the group is done with stage s: refill it
             if (gtid == 0 && item + S < n_items) { fence_proxy_async(); issue(item + S); }
         }
+    }
+}
+
+// k_col_xty_slabs: the multi-slab form (N > 384 rows: a tile's accumulators live across its slabs). Items = (tile, slab) of the
+// block's tile range in order, all 8 warps on the same item; reduction over rows is split over warps.
+template <int NT, bool MASKED, bool RESIDENT_U>
+__global__ void __launch_bounds__(THREADS, 1) k_col_xty_slabs(StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    int t0, t1;
+    split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
+    const int n_items = (t1 - t0) * a.n_slabs;
+    const int S = a.n_stages;
+
+    const int ysz = TG * a.pitchS;
+    const int usz = a.KP * a.pitchU;
+    const int stage_doubles = ysz + (RESIDENT_U ? 0 : usz);
+    double* Ures = reinterpret_cast<double*>(smem_raw);                       // resident Ut (if any)
+    double* stage0 = Ures + (RESIDENT_U ? usz : 0);
+    double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [NWARPS][NT*2*64] when scratch_sep
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers + 1 for Ut
+
+    if (tid == 0) {
+        for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        const int64_t gene = (int64_t)tile * TG;
+        const uint32_t ybytes = (uint32_t)rows_here * 8u;
+        uint32_t total = ybytes * TG;
+        if (!RESIDENT_U) total += (uint32_t)a.KP * ybytes;
+        mbar_expect_tx(&bars[s], total);
+        if (a.pitchS == a.ldY && rows_here == a.ldY) {
+            tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
+        } else {
+            for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
+        }
+        if (!RESIDENT_U) {
+            double* Us = Ys + ysz;
+            for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, ybytes, &bars[s]);
+        }
+    };
+    if (tid == 0) {
+        if (RESIDENT_U) {
+            mbar_expect_tx(&bars[S], (uint32_t)usz * 8u);
+            tma_load_1d(Ures, a.Ut, (uint32_t)usz * 8u, &bars[S]);
+        }
+        for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
+    }
+    if (RESIDENT_U) mbar_wait(&bars[S], 0);
+
+    double acc[NT][2][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) acc[n][m][0] = acc[n][m][1] = 0.0;
+
+    for (int item = 0; item < n_items; ++item) {
+        const int s = item % S;
+        double* Ys = stage0 + (size_t)s * stage_doubles;
+        const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
+        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int r0 = slab * a.R;
+        const int rows_here = min(a.R, a.ldY - r0);
+        if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
+        uint32_t word = 0;
+        if (MASKED) {
+            const int c = tid >> 4, w = tid & 15;
+            if (32 * w < rows_here) word = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
+        }
+        mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
+        if (MASKED) {
+            premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
+            __syncthreads();
+        }
+        const int KS = rows_here >> 2;
+        int k0, k1;
+        split_range(KS, NWARPS, warp, k0, k1);
+        for (int ks = k0; ks < k1; ++ks) {
+            double av[NT], bv[2];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) av[n] = Us[(8 * n + g) * a.pitchU + 4 * ks + t];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) bv[m] = Ys[(8 * m + g) * a.pitchS + 4 * ks + t];
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) dmma(acc[n][m][0], acc[n][m][1], av[n], bv[m]);
+        }
+        if (slab == a.n_slabs - 1) {
+            // cross-warp reduction in a fixed order, then store the K x 16 tile of Xty. The scratch
+            // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer when that is large enough.
+            double* scratch = a.scratch_sep ? scratch_own : Ys;
+            __syncthreads();
+            double* sc = scratch + warp * (NT * 2 * 64);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[n][m][0];
+                    sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[n][m][1];
+                    acc[n][m][0] = acc[n][m][1] = 0.0;
+                }
+            __syncthreads();
+            for (int x = tid; x < NT * 2 * 64; x += THREADS) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
+                const int tl = x >> 6, ln = (x & 63) >> 1, e = x & 1;
+                const int n = tl >> 1, m = tl & 1;
+                const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
+                if (k < a.ldV) a.out[((int64_t)tile * TG + gene) * a.ldV + k] = sum;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -571,13 +701,16 @@ void launch_col_xty(const Geom& g, bool masked, const double* Y, const uint32_t*
     const size_t stage = ((size_t)TG * a.pitchS + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
     a.scratch_sep = (stage / 8 < need) ? 1 : 0;
     const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + 8 * 8 + (a.scratch_sep ? need * 8 : 0);
-#define LAUNCH_CX(NTv, M, RS) { set_smem(k_col_xty<NTv, M, RS>, smem); k_col_xty<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a); }
+    // single slab with U^T resident: two-group kernel; row slabs (N > 384): all warps on one item, accumulators across slabs
+#define LAUNCH_CX(NTv, M) { set_smem(k_col_xty<NTv, M, true>, smem); k_col_xty<NTv, M, true><<<n_blocks, THREADS, smem, st>>>(a); }
+#define LAUNCH_CS(NTv, M) { set_smem(k_col_xty_slabs<NTv, M, false>, smem); k_col_xty_slabs<NTv, M, false><<<n_blocks, THREADS, smem, st>>>(a); }
 #define LAUNCH_CX2(NTv)                                                       \
-    if (masked) { if (res) LAUNCH_CX(NTv, true, true) else LAUNCH_CX(NTv, true, false) } \
-    else { if (res) LAUNCH_CX(NTv, false, true) else LAUNCH_CX(NTv, false, false) }
+    if (masked) { if (res) LAUNCH_CX(NTv, true) else LAUNCH_CS(NTv, true) } \
+    else { if (res) LAUNCH_CX(NTv, false) else LAUNCH_CS(NTv, false) }
     switch (g.NT) { case 1: LAUNCH_CX2(1) break; case 2: LAUNCH_CX2(2) break; case 3: LAUNCH_CX2(3) break; default: LAUNCH_CX2(4) break; }
 #undef LAUNCH_CX2
 #undef LAUNCH_CX
+#undef LAUNCH_CS
 }
 
 void launch_sse(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const uint32_t* teC, const double* Ut, const double* V,

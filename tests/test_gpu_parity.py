@@ -127,6 +127,20 @@ def test_multi_slab_rows(ctx):
             assert_parity(res, fac, ro, tuning)
 
 
+def test_multi_slab_rows_several_gene_tiles_per_block(ctx):
+    """N > 384 AND more gene tiles (16 genes) than SMs: every block of the streaming kernels walks several tiles, each over
+    several row slabs, through its stage ring (the geometry of the 17382 x 56200 configuration; a stage hand-over bug between
+    tiles stalled exactly this case and no smaller shape reaches it)."""
+    N, P, K = 1000, 5000, 4                    # 8 row slabs of 128 through a 4-stage ring, 313 gene tiles on 148 blocks
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=31, seed=N)
+    tr, te = synth.random_masks(N, P, 0.1, 1)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=2)
+    for tuning, alpha in ((0, 0.0), (1, 0.0), (0, 0.4)):
+        ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 4.0, 4.0, alpha, tuning, 1e-12, 1e-5, 2, perm_mode=1, seed=8)
+        res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 4.0, alpha, tuning, 2, 8)
+        assert_parity(res, fac, ro, tuning)
+
+
 def test_mask_dtypes_and_heavy_masking(ctx):
     """int32 (R integer), uint8 and double masks give identical results; rows/genes that are almost fully masked."""
     N, P, K = 64, 96, 7

@@ -187,6 +187,10 @@ def run_ours(args, w, rank, world, local):
     ctx.set_profile(False)
 
     # ---- end to end through the one-shot C-ABI call with host buffers (H2D of Y/masks/factors and D2H of factors inside)
+    # one untimed one-shot call of a single iteration first: the call allocates its device buffers and instantiates its CUDA
+    # graphs anew every time, and the first such call in a process also grows the driver's memory pools (measured: 0.11 s
+    # against 0.24 s for the same 25 iterations)
+    ctx.optimize(prob, _cabi.HostFactors(F0, V0, K), opts(0))
     barrier()
     fac_e = _cabi.HostFactors(F0, V0, K)
     t0 = time.perf_counter()
@@ -276,7 +280,7 @@ def run_ours(args, w, rank, world, local):
                        "timed_iterations": f"0..{args.steps - 1} from N(0,0.001^2) init", "parallelism": f"gene-sharded x{world}",
                        "l2": "Y (134 MB) exceeds L2 at N=1; at N>1 the shard is L2-resident in the real fit too (no flush between iterations)"},
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": oe["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "device_loop_seconds": oe["loop_ms"] * 1e-3, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y"},
+                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "device_loop_seconds": oe["loop_ms"] * 1e-3, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y; one untimed 1-iteration call of the same entry point first"},
             "gpu_launches": int(out["kernel_launches"]),
             "clocks": sampler.summary(),
             "roofline": roof_dom or roof_iter,

@@ -1,0 +1,114 @@
+"""Host-side model of the stage hand-over protocol of k_col_xty (insider_b200/csrc/k_stream.cu): two warp groups take
+alternate gene tiles from ONE ring of S shared-memory stages; item i + S is issued into item i's stage by the group that
+consumed item i; a consumer waits for its item with an mbarrier PARITY wait.
+
+A parity wait can only tell the barrier's current phase from the one before it. The model reproduces the failure that
+stalled the 17382 x 56200 configuration in round 1 (a group whose first item lies several phases ahead passes the wait
+on stale data) and checks the two remedies the kernel uses: the issued[] guard, and sending multi-slab shapes to the
+all-warps kernel (one group). Pure Python, no GPU: random schedules of the asynchronous loads and of the two groups.
+"""
+import random
+
+import pytest
+
+
+class Ring:
+    def __init__(self, S, n_items):
+        self.S, self.n_items = S, n_items
+        self.completed = [0] * S          # phases completed per stage barrier
+        self.pending = [[] for _ in range(S)]
+        self.content = [None] * S         # item whose data sits in the stage
+        self.issued = [-1] * S
+
+    def issue(self, item):
+        s = item % self.S
+        self.pending[s].append(item)
+        self.issued[s] = item
+
+    def land_one(self, rng):
+        ready = [s for s in range(self.S) if self.pending[s]]
+        if not ready:
+            return False
+        s = rng.choice(ready)
+        self.content[s] = self.pending[s].pop(0)
+        self.completed[s] += 1
+        return True
+
+    def try_wait(self, s, parity):
+        # mbarrier.try_wait.parity: true iff the phase BEFORE the current one has this parity (phase -1 counts as odd)
+        return ((self.completed[s] - 1) & 1) == parity
+
+
+def run(S, n_tiles, n_slabs, n_groups, guard, seed, max_steps=200000):
+    """Returns (ok, reason). Each group walks its tiles (tile index % n_groups), all slabs of a tile in order."""
+    rng = random.Random(seed)
+    n_items = n_tiles * n_slabs
+    ring = Ring(S, n_items)
+    for i in range(min(S, n_items)):
+        ring.issue(i)
+    todo = [[tl * n_slabs + sl for tl in range(g, n_tiles, n_groups) for sl in range(n_slabs)] for g in range(n_groups)]
+    pos = [0] * n_groups
+    busy = [0] * n_groups                 # remaining compute steps of the item being consumed
+    for _ in range(max_steps):
+        if all(pos[g] == len(todo[g]) for g in range(n_groups)):
+            return True, "done"
+        actor = rng.randrange(n_groups + 1)
+        if actor == n_groups:
+            ring.land_one(rng)
+            continue
+        g = actor
+        if pos[g] == len(todo[g]):
+            continue
+        item = todo[g][pos[g]]
+        s = item % S
+        if busy[g] == 0:
+            if guard and ring.issued[s] < item:
+                continue                                        # spin on issued[]
+            if not ring.try_wait(s, (item // S) & 1):
+                continue                                        # spin on the barrier
+            if ring.content[s] != item:
+                return False, f"group {g} consumed stage {s} holding item {ring.content[s]} as item {item}"
+            busy[g] = rng.randrange(1, 4)
+        else:
+            busy[g] -= 1
+            if busy[g] == 0:
+                pos[g] += 1
+                if item + S < n_items:
+                    ring.issue(item + S)                        # the consumer refills its stage
+    return False, "no progress (deadlock)"
+
+
+@pytest.mark.parametrize("S", [2, 3, 4])
+@pytest.mark.parametrize("n_tiles", [1, 2, 3, 7, 20])
+def test_two_groups_single_slab_with_guard(S, n_tiles):
+    """The shape k_col_xty runs: n_slabs == 1, two groups, issued[] guard."""
+    for seed in range(40):
+        ok, why = run(S, n_tiles, 1, 2, True, seed)
+        assert ok, why
+
+
+@pytest.mark.parametrize("n_slabs", [2, 4, 8, 136])
+def test_guard_also_covers_multi_slab(n_slabs):
+    """With the guard the protocol is correct for any geometry (the groups then take turns, which is why multi-slab shapes
+    use the one-group kernel instead: correctness is not the reason)."""
+    for seed in range(10):
+        ok, why = run(4, 5, n_slabs, 2, True, seed)
+        assert ok, why
+
+
+def test_unguarded_two_groups_alias_phases_on_multi_slab():
+    """The bug: group 1's first item (index n_slabs) is an even number of phases ahead of what its stage has seen, the
+    parity wait passes on item 0's data."""
+    bad = 0
+    for seed in range(20):
+        ok, why = run(4, 5, 8, 2, False, seed)
+        bad += (not ok)
+    assert bad > 0
+
+
+@pytest.mark.parametrize("n_slabs", [1, 3, 8])
+def test_one_group_in_order_needs_no_guard(n_slabs):
+    """k_col_xty_slabs / k_row_b / k_sse: all warps consume every item in order; the plain parity wait is exact."""
+    for seed in range(20):
+        ok, why = run(4, 6, n_slabs, 1, False, seed)
+        assert ok, why

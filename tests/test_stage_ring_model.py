@@ -112,3 +112,12 @@ def test_one_group_in_order_needs_no_guard(n_slabs):
     for seed in range(20):
         ok, why = run(4, 6, n_slabs, 1, False, seed)
         assert ok, why
+
+
+def test_unguarded_single_slab_odd_ring_can_alias():
+    """Why the guard is there even for n_slabs == 1: with an odd number of stages (S = 3 at 377 x 44477) item i - S belongs to
+    the OTHER group, nothing orders this group's wait for item i after that item's load, and a slow load lets the parity wait
+    pass one phase early. Even rings hand a stage back to the same group and are safe without the guard."""
+    assert sum(not run(3, 20, 1, 2, False, seed)[0] for seed in range(200)) > 0
+    assert sum(not run(2, 20, 1, 2, False, seed)[0] for seed in range(200)) == 0
+    assert sum(not run(4, 20, 1, 2, False, seed)[0] for seed in range(200)) == 0

@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the INSIDER alternating-optimisation fit on B200 (BASELINE.json metric: ALS iterations/s on the
-ageing-shaped 377 x 44477, K = 23 fit, next to the CPU path).
+"""Benchmark of the INSIDER alternating-optimisation fit on B200 (BASELINE.json metric: ALS iterations/s and
+time-to-global_tol on the ageing-shaped 377 x 44477, K = 23 fit, next to the CPU path).
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...   # the restated reference (oracle port) on the host cores
+  python bench.py --workload ageing_full_377x44477_K23_tune --gpus N    # tune() grid (51 fits) as replicas over N GPUs
 
 A "step" is one ALS iteration (src/optimize.cpp:325-410). The timed region is iterations 0..K-1 of the fit from the
 standard N(0, 0.001^2) initialisation (the per-iteration cost of this algorithm depends on the iteration index: the
-elastic-net solver needs hundreds of sweeps per gene in the first iterations); the W warm-up steps run the same
+elastic-net solver needs thousands of sweeps per gene in the first iterations); the W warm-up steps run the same
 kernels on the same data in a throw-away session first. Genes are sharded across ranks (strong scaling: the matrix is
 fixed); the only exchange is the all-reduce of the row-side sufficient statistics.
+
+Untimed-by-the-driver extra legs of the default run (each reported in the JSON line): per-kernel device times of the same
+K iterations, end to end from pinned and from pageable host memory, steady-state iterations, time-to-global_tol, a small
+multi-rank fit compared with the CPU oracle (parity_check), the CPU baseline on a bounded sample (N = 1 only).
 """
 from __future__ import annotations
 
@@ -28,17 +33,28 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1]: full ageing-shaped synthetic, fit() => tuning = 0 (R/insider.R:190 partition = 0)
     "ageing_full_377x44477_K23_fit": dict(N=377, P=44477, K=23, lam=10.0, alpha=0.4, tuning=0),
+    # BASELINE.json configs[2]: the tune() grid on the same shape (tuning = 1), run as replicas
     "ageing_full_377x44477_K23_tune": dict(N=377, P=44477, K=23, lam=10.0, alpha=0.4, tuning=1),
+    "ageing_full_377x44477_K23_masked": dict(N=377, P=44477, K=23, lam=10.0, alpha=0.4, tuning=1),
     "ageing_toy_377x5000_K23_fit": dict(N=377, P=5000, K=23, lam=10.0, alpha=0.4, tuning=0),
 }
-CPU_SAMPLE_GENES = 2048
+CPU_SAMPLE_GENES = 4096
+FP64_PEAK = 37.1   # TFLOP/s, FP64 pipe peak measured on this pool by tools/microbench.cu (profiles/r01_microbench_fp64_hbm.txt)
+CD_FLOPS_PER_UPDATE = lambda K: 2.0 * K + 12.0   # noqa: E731  (q update 2K + scalar chain 12)
 
 
 def bytes_per_iter(N, P, K, tuning):
-    """SURVEY.md §8(d): algorithmic bytes per ALS iteration (two passes over Y, masks at 1 bit, V 3x, U 2x)."""
+    """SURVEY.md 8(d): algorithmic bytes per ALS iteration (two passes over Y, masks at 1 bit, V 3x, U 2x)."""
     if tuning == 1:
         return 2 * (8 * N * P + N * P / 8) + N * P / 8 + 3 * 8 * K * P + 2 * 8 * N * K
     return 2 * 8 * N * P + 3 * 8 * K * P + 2 * 8 * N * K
+
+
+def config_for(args, w):
+    """The workload description, IDENTICAL in both arms (ours / --impl reference)."""
+    return {"workload": args.workload, **{k: w[k] for k in ("N", "P", "K", "lam", "alpha", "tuning")},
+            "timed_iterations": f"0..{args.steps - 1} from N(0,0.001^2) init", "parallelism": "gene-sharded",
+            "l2": "no flush: Y (134 MB) exceeds the 126 MB L2 at N=1; at N>1 the shard is L2-resident in the real fit too"}
 
 
 class ClockSampler(threading.Thread):
@@ -69,7 +85,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def summary(self):
         s = sorted(self.samples)
@@ -87,66 +103,132 @@ def make_problem(w, P=None):
     return pb, tr, te, F0, V0
 
 
+def cpu_oracle(n_threads=None):
+    """The oracle for a TIMED CPU leg: -march=native build compiled on this host, explicit OpenMP team (torchrun exports
+    OMP_NUM_THREADS=1). Returns (module, team size really in effect, build kind)."""
+    from oracle import oracle
+    native = oracle.use_native()
+    team = oracle.set_threads(n_threads or (os.cpu_count() or 1))
+    return oracle, team, ("-O3 -march=native" if native else "-O3 -march=x86-64-v3 (native build failed)")
+
+
+def time_cpu(oracle, team, w, P, steps):
+    pb, tr, te, F0, V0 = make_problem(w, P=P)
+    r = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, w["K"], w["lam"], w["lam"], w["alpha"], w["tuning"], 1e-12, 1e-5,
+                        steps - 1, perm_mode=1, seed=1, n_cores_row=team, n_cores_col=team)
+    return r
+
+
 def run_reference(args, w, rank):
-    """The restated reference (oracle/insider_oracle.cpp, OpenMP) on the host cores: K iterations from the same
-    initialisation on a bounded sample (the first CPU_SAMPLE_GENES genes); value scaled to the full gene count."""
+    """The restated reference (oracle/insider_oracle.cpp, OpenMP) on the host cores: the same K iterations from the same
+    initialisation on the FULL gene set - measured, not extrapolated."""
     if rank != 0:
         return
-    from oracle import oracle
-    cores = os.cpu_count() or 1
-    Ps = min(CPU_SAMPLE_GENES, w["P"])
-    pb, tr, te, F0, V0 = make_problem(w, P=Ps)
-    if args.warmup > 0:
-        oracle.optimize(pb.Y[:, :64], F0, V0[:, :64], pb.confounder, None, None if tr is None else tr[:, :64], None if te is None else te[:, :64],
-                        0, w["K"], w["lam"], w["lam"], w["alpha"], w["tuning"], 1e-12, 1e-5, 0, perm_mode=1, seed=1, n_cores_row=cores, n_cores_col=cores)
-    r = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, w["K"], w["lam"], w["lam"], w["alpha"], w["tuning"], 1e-12, 1e-5,
-                        args.steps - 1, perm_mode=1, seed=1, n_cores_row=cores, n_cores_col=cores)
+    oracle, team, flags = cpu_oracle()
+    if args.warmup > 0:     # warm-up: thread team start-up, page faults of the allocator (small sample; the fit itself has no cache to warm)
+        time_cpu(oracle, team, w, 256, min(args.warmup, 2))
+    P = args.ref_genes or w["P"]
+    t0 = time.perf_counter()
+    r = time_cpu(oracle, team, w, P, args.steps)
+    wall = time.perf_counter() - t0
     secs = r.seconds_in_loop
-    value = args.steps / secs * (Ps / w["P"])
-    sample = f"first {Ps} of {w['P']} genes, iterations 0..{args.steps - 1}; iterations/s scaled by {Ps}/{w['P']} (cost is linear in genes)"
+    value = args.steps / secs * (P / w["P"])
+    sample = (f"all {w['P']} genes, iterations 0..{args.steps - 1} (measured, no extrapolation)" if P == w["P"] else
+              f"first {P} of {w['P']} genes, iterations 0..{args.steps - 1}; EXTRAPOLATED by {P}/{w['P']}")
     line = {"impl": "reference", "metric": "als_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: w[k] for k in ("N", "P", "K", "lam", "alpha", "tuning")}},
-            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample,
-                             "sample_seconds": secs, "cd_sweeps_per_gene_iter": r.cd_sweeps / Ps / args.steps},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_for(args, w),
+            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": team, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample,
+                             "extrapolated": P != w["P"], "sample_seconds": secs, "wall_seconds_incl_setup": wall, "build": flags,
+                             "cd_sweeps_per_gene_iter": r.cd_sweeps / P / args.steps, "loss_after_timed": r.loss},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing (rendezvous, barrier, max over ranks); the data path's only collective is the library's own."""
+
+    def __init__(self, rank, world, local):
+        import torch
+        self.torch, self.rank, self.world, self.local = torch, rank, world, local
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; libinsider_b200 has no CPU fallback")
+        torch.cuda.set_device(local)
+        if world > 1:
+            import torch.distributed as tdist
+            tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            self.td = tdist
+
+    def barrier(self):
+        if self.world > 1:
+            self.td.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, x, op="max"):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX if op == "max" else self.td.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_array(self, a):
+        """all ranks' float64 arrays of identical shape, stacked on a new leading axis"""
+        if self.world == 1:
+            return a[None]
+        t = self.torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.td.all_gather(out, t)
+        return np.stack([o.cpu().numpy() for o in out])
+
+    def close(self):
+        if self.world > 1:
+            self.td.destroy_process_group()
+
+
+def parity_check(ctx, dist):
+    """A small gene-sharded fit on ALL ranks against the CPU oracle on rank 0 (both tunings): carries multi-GPU parity
+    evidence in the bench line (the driver's test box has one GPU). Untimed."""
+    from insider_b200 import _cabi, synth
+    N, P, K, iters = 96, 1024, 10, 10
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=17, seed=5)
+    tr, te = synth.random_masks(N, P, 0.1, 6)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=7)
+    out = {"shape": f"{N}x{P} K={K}, {iters + 1} iterations, lambda=3 alpha=0.4, world={dist.world}"}
+    for tuning in (0, 1):
+        prob = _cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0)
+        fac = _cabi.HostFactors(F0, V0, K)
+        opt = _cabi.default_options()
+        opt.lambda1 = opt.lambda2 = 3.0
+        opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = 0.4, tuning, 1e-9, 1e-5, iters, 9
+        rg = ctx.optimize(prob, fac, opt)
+        sweeps = dist.reduce(float(rg["cd_sweeps"]), "sum")
+        if dist.rank == 0:
+            from oracle import oracle
+            oracle.set_threads(min(8, os.cpu_count() or 1))
+            ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 3.0, 3.0, 0.4, tuning, 1e-9, 1e-5, iters, perm_mode=1, seed=9)
+            dv = float(np.abs(fac.V - ro.column_factor).max() / np.abs(ro.column_factor).max())
+            da = float(max(np.abs(a - b).max() / np.abs(b).max() for a, b in zip(fac.factors, ro.factors)))
+            dl = float(abs(rg["loss"] - ro.loss) / abs(ro.loss))
+            out[f"tuning{tuning}"] = {"dV": dv, "dA": da, "dloss": dl, "iters_equal": rg["iters_run"] == ro.iters_run,
+                                      "sweeps_equal": int(sweeps) == ro.cd_sweeps, "ok": bool(dv < 1e-8 and da < 1e-8 and dl < 1e-10)}
+    return out
+
+
 def run_ours(args, w, rank, world, local):
-    import torch
     from insider_b200 import _cabi, dist as ibdist
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libinsider_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as tdist
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist = Dist(rank, world, local)
+    torch = dist.torch
     ctx = ibdist.make_context(local)
     pb, tr, te, F0, V0 = make_problem(w)
     N, P, K = w["N"], w["P"], w["K"]
 
-    def opts(max_iter):
+    def opts(max_iter, gtol=1e-12):
         o = _cabi.default_options()
         o.lambda1 = o.lambda2 = w["lam"]
-        o.alpha, o.tuning, o.global_tol, o.sub_tol, o.max_iter, o.seed = w["alpha"], w["tuning"], 1e-12, 1e-5, max_iter, 1
+        o.alpha, o.tuning, o.global_tol, o.sub_tol, o.max_iter, o.seed = w["alpha"], w["tuning"], gtol, 1e-5, max_iter, 1
         return o
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as tdist
-            tdist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        import torch.distributed as tdist
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-        return float(t.item())
 
     # pinned host copy of Y for the end-to-end leg
     Yp = torch.empty((P, N), dtype=torch.float64, pin_memory=True)       # row-major (P, N) == column-major (N, P)
@@ -165,48 +247,66 @@ def run_ours(args, w, rank, world, local):
     sampler = ClockSampler(local)
     fac = _cabi.HostFactors(F0, V0, K)
     s = res.begin(fac, opts(10 ** 6))
-    barrier()
+    dist.barrier()
     sampler.start()
     t_wall = time.perf_counter()
     done, ms = s.step(args.steps)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall
-    barrier()
+    dist.barrier()
     sampler.stop_flag = True
     out = s.end(read_factors=False)
-    ms = max_over_ranks(ms)
+    ms = dist.reduce(ms)
     value = args.steps / (ms * 1e-3)
 
-    # ---- per-kernel device times (separate short profiled session; not part of the timed number)
+    # ---- per-kernel device times of the SAME iterations 0..K-1 (separate profiled session: plain launches, one event pair per kernel)
     ctx.set_profile(True)
     sp = res.begin(_cabi.HostFactors(F0, V0, K), opts(10 ** 6))
-    n_prof = min(args.steps, 12)
+    n_prof = args.steps
     sp.step(n_prof)
     prof = sp.profile()
     outp = sp.end(read_factors=False)
     ctx.set_profile(False)
 
-    # ---- end to end through the one-shot C-ABI call with host buffers (H2D of Y/masks/factors and D2H of factors inside)
-    # one untimed one-shot call of a single iteration first: the call allocates its device buffers and instantiates its CUDA
-    # graphs anew every time, and the first such call in a process also grows the driver's memory pools (measured: 0.11 s
-    # against 0.24 s for the same 25 iterations)
+    # ---- end to end through the one-shot C-ABI call with host buffers (H2D of Y/masks/factors and D2H of factors inside).
+    # One untimed one-shot call of a single iteration first: the call allocates its device buffers and instantiates its CUDA
+    # graphs anew every time, and the first such call in a process also grows the driver's memory pools.
     ctx.optimize(prob, _cabi.HostFactors(F0, V0, K), opts(0))
-    barrier()
-    fac_e = _cabi.HostFactors(F0, V0, K)
+    dist.barrier()
     t0 = time.perf_counter()
-    oe = ctx.optimize(prob, fac_e, opts(args.steps - 1))
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = args.steps / t_e2e
+    oe = ctx.optimize(prob, _cabi.HostFactors(F0, V0, K), opts(args.steps - 1))
+    t_e2e = dist.reduce(time.perf_counter() - t0)
+    # the same from PAGEABLE host memory (what R hands over)
+    prob_pg = _cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0)
+    dist.barrier()
+    t0 = time.perf_counter()
+    ctx.optimize(prob_pg, _cabi.HostFactors(F0, V0, K), opts(args.steps - 1))
+    t_e2e_pg = dist.reduce(time.perf_counter() - t0)
 
     # ---- steady-state iterations (late phase of the fit: a few sweeps per gene); every rank takes part
     ms_late = None
     if not args.no_late:
         sl = res.begin(_cabi.HostFactors(F0, V0, K), opts(10 ** 6))
         sl.step(args.late_start)
-        barrier()
+        dist.barrier()
         _, ms_late = sl.step(20)
         sl.end(read_factors=False)
-        ms_late = max_over_ranks(ms_late)
+        ms_late = dist.reduce(ms_late)
+
+    # ---- time to global_tol (the other half of BASELINE.json's metric): whole resident fit, wall clock between barriers
+    ttt = []
+    if not args.no_ttt:
+        for gtol, max_iter in ((1e-7, 50000), (1e-9, 50000)):
+            dist.barrier()
+            t0 = time.perf_counter()
+            o = res.optimize(_cabi.HostFactors(F0, V0, K), opts(max_iter, gtol))
+            torch.cuda.synchronize()
+            secs = dist.reduce(time.perf_counter() - t0)
+            ttt.append({"global_tol": gtol, "max_iter": max_iter, "seconds": secs, "iters_run": o["iters_run"],
+                        "converged": bool(o["iters_run"] <= max_iter), "device_loop_seconds": o["loop_ms"] * 1e-3,
+                        "final_loss": o["loss"], "ms_per_iteration": 1e3 * secs / max(1, o["iters_run"])})
+
+    pc = parity_check(ctx, dist) if not args.no_parity else None
 
     if rank == 0:
         peaks = {}
@@ -221,7 +321,7 @@ def run_ours(args, w, rank, world, local):
         Pl = ibdist.gene_block(P, world, 0)[1]
         kern = {}
         for name, (kms, calls) in prof.items():
-            kern[name] = {"ms_total": kms, "calls": calls, "us_per_call": 1e3 * kms / max(1, calls)}
+            kern[name] = {"ms_total": kms, "calls": calls, "us_per_call": 1e3 * kms / max(1, calls), "ms_per_step": kms / n_prof}
         tot_prof = sum(v["ms_total"] for v in kern.values()) or 1.0
         for v in kern.values():
             v["share"] = v["ms_total"] / tot_prof
@@ -232,42 +332,31 @@ def run_ours(args, w, rank, world, local):
             if kname in kern:
                 stream[kname] = {"algorithmic_bytes": y_bytes, "GBps": y_bytes / (kern[kname]["us_per_call"] * 1e-6) / 1e9,
                                  "frac_of_hbm_peak": y_bytes / (kern[kname]["us_per_call"] * 1e-6) / 1e9 / hbm_peak}
-        # dominant kernel: the persistent elastic-net solver. Algorithmic FP64 flops per coordinate update: 2K for the
-        # q -= delta * XtX[:,k] update + 12 for the soft-threshold / exact division / loss-decrement chain.
-        FP64_PEAK = 37.1   # TFLOP/s, measured on this pool by tools/microbench.cu (profiles/r01_microbench_fp64_hbm.txt)
+        # dominant kernel: the elastic-net solver. Algorithmic FP64 flops per coordinate update: 2K for the q update + 12 for
+        # the soft-threshold / division / loss-decrement chain.
         cd = None
-        cd_name = "k_cd_dense" if "k_cd_dense" in kern else ("k_col_solve" if "k_col_solve" in kern else None)
+        cd_name = next((n for n in ("k_cd_dense", "k_cd_masked", "k_col_solve") if n in kern), None)
         if cd_name:
             steps_cd, sweeps = outp["cd_steps"], outp["cd_sweeps"]
             secs = kern[cd_name]["ms_total"] * 1e-3
-            flops = steps_cd * (2.0 * K + 12.0)
+            flops = steps_cd * CD_FLOPS_PER_UPDATE(K)
             cd = {"kernel": cd_name, "gene_sweeps": sweeps, "coordinate_updates": steps_cd, "gene_sweeps_per_s": sweeps / secs,
                   "algorithmic_flops": flops, "fp64_tflops": flops / secs / 1e12, "fp64_peak_tflops_measured": FP64_PEAK,
-                  "share_of_iteration": kern[cd_name]["share"]}
+                  "share_of_iteration": kern[cd_name]["share"], "ms_per_step": kern[cd_name]["ms_per_step"]}
         roof_dom = None
         if cd:
-            note = ("thread-per-gene coordinate descent, K=23: every step needs the 24-double table row in every thread; ncu shows the "
-                    "shared-memory data pipe at 92 % of peak (l1tex__throughput) with the FP64 pipe at 42 %; lockstep warps run until their "
-                    "slowest gene converges (lane efficiency ~0.8 with phased re-grouping / ordering by the previous counts). "
-                    "See profiles/r01_ncu_k_cd_dense_v5_dense_A.txt, r01_cd_phases.txt"
-                    if cd_name == "k_cd_dense" else
-                    "8-lanes-per-gene coordinate descent with per-gene Gram matrices: bound by the shared-memory pipe; "
-                    "see profiles/r01_ncu_k_cd_persistent_*.txt")
-            # dram__bytes_read.sum + dram__bytes_write.sum of one whole-problem launch from the ncu --set full capture of this
-            # command's shape (profiles/r01_ncu_k_cd_dense_v5_dense_A.txt: 20.37 MB read, 0 written; algorithmic Xty + V = 18.6 MB;
-            # the phase launches of iterations 0-2 read their share of it)
-            traffic = 20372224 if (cd_name == "k_cd_dense" and world == 1 and args.workload == "ageing_full_377x44477_K23_fit") else None
-            roof_dom = {"bound": "tensor", "kernel": cd_name, "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
-                        "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": traffic,
+            roof_dom = {"bound": "fp64", "limiter": "FP64 CUDA-core pipe (DFMA chain, no tensor-core form); see DESIGN.md 4 for the ncu reading",
+                        "kernel": cd_name, "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
+                        "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK, "traffic": None,
                         "peak_source": "FP64 pipe peak measured with DMMA m8n8k4 by tools/microbench.cu on this pool's B200 (MEASURED_PEAKS.json has "
                                        "no FP64 entry; its bf16 tensor peak does not apply to an FP64 path)",
-                        "note": note,
                         "algorithmic_flops_per_launch": flops / max(1, kern[cd_name]["calls"]),
-                        "avg_launch_ms": kern[cd_name]["ms_total"] / max(1, kern[cd_name]["calls"])}
+                        "avg_launch_ms": kern[cd_name]["ms_total"] / max(1, kern[cd_name]["calls"]),
+                        "launches": kern[cd_name]["calls"], "kernel_ms_per_step": kern[cd_name]["ms_per_step"],
+                        "profiled_iterations": f"0..{n_prof - 1} (the timed region's)"}
         roof_iter = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_iteration": b_iter,
                      "what": "whole ALS iteration, SURVEY.md 8(d) bytes / mean iteration time (per GPU)", "dominant_kernel": dominant}
-        # steady-state iterations (late phase of the fit: a few sweeps per gene), for context
         late = None
         if ms_late is not None:
             late = {"iterations": f"{args.late_start}..{args.late_start + 19}", "ms_per_iteration": ms_late / 20,
@@ -275,39 +364,126 @@ def run_ours(args, w, rank, world, local):
         line = {
             "metric": "als_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: w[k] for k in ("N", "P", "K", "lam", "alpha", "tuning")},
-                       "timed_iterations": f"0..{args.steps - 1} from N(0,0.001^2) init", "parallelism": f"gene-sharded x{world}",
-                       "l2": "Y (134 MB) exceeds L2 at N=1; at N>1 the shard is L2-resident in the real fit too (no flush between iterations)"},
-            "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": oe["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "device_loop_seconds": oe["loop_ms"] * 1e-3, "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y; one untimed 1-iteration call of the same entry point first"},
+            "dtype": "f64", "data": "synthetic", "config": config_for(args, w),
+            "e2e": {"value": args.steps / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": oe["h2d_bytes"] / args.steps,
+                    "d2h_bytes_per_step": oe["d2h_bytes"] / args.steps, "seconds": t_e2e, "device_loop_seconds": oe["loop_ms"] * 1e-3,
+                    "what": "insider_b200_optimize (one-shot C ABI) from pinned host Y; one untimed 1-iteration call of the same entry point first"},
+            "e2e_pageable": {"value": args.steps / t_e2e_pg, "unit": "iterations/s", "seconds": t_e2e_pg,
+                             "what": "the same call from pageable host memory (what R passes)"},
             "gpu_launches": int(out["kernel_launches"]),
             "clocks": sampler.summary(),
             "roofline": roof_dom or roof_iter,
             "roofline_iteration_hbm": roof_iter,
             "roofline_kernels": {"streaming": stream, "coordinate_descent": cd, "kernels": kern, "profiled_iterations": n_prof},
             "late_phase": late,
+            "time_to_global_tol": ttt,
+            "parity_check": pc,
             "cd_sweeps_per_gene_iter": out["cd_sweeps"] / max(1, Pl) / args.steps,
             "loss_after_timed": out["loss"], "wall_s_timed_region": t_wall,
         }
-        # CPU baseline beside it (rank 0, N = 1 only): the restated reference on a bounded sample
+        # CPU baseline beside it (rank 0, N = 1 only): the restated reference on a bounded sample of the same workload
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle
-            cores = os.cpu_count() or 1
+            oracle, team, flags = cpu_oracle()
             Ps = min(CPU_SAMPLE_GENES, P)
-            pbs, trs, tes, F0s, V0s = make_problem(w, P=Ps)
-            r = oracle.optimize(pbs.Y, F0s, V0s, pbs.confounder, None, trs, tes, 0, K, w["lam"], w["lam"], w["alpha"], w["tuning"], 1e-12, 1e-5,
-                                args.steps - 1, perm_mode=1, seed=1, n_cores_row=cores, n_cores_col=cores)
+            r = time_cpu(oracle, team, w, Ps, args.steps)
             v = args.steps / r.seconds_in_loop * (Ps / P)
-            line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
-                                    "sample": f"first {Ps} of {P} genes, iterations 0..{args.steps - 1}, scaled by {Ps}/{P}",
-                                    "sample_seconds": r.seconds_in_loop}
+            line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": team, "host_cpus": os.cpu_count(), "kind": "port", "build": flags,
+                                    "sample": f"first {Ps} of {P} genes, iterations 0..{args.steps - 1}; scaled by {Ps}/{P} (bounded sample; "
+                                              "`bench.py --impl reference` measures the full gene set)",
+                                    "extrapolated": True, "sample_seconds": r.seconds_in_loop}
         print(json.dumps(line), flush=True)
     res.release()
     ctx.close()
-    if world > 1:
-        import torch.distributed as tdist
-        tdist.destroy_process_group()
+    dist.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def tune_grid(w):
+    """BASELINE.json configs[2] (README.md:79): latent_dimension 10..30 step 2 at (0.1, 0.1, 0), then lambda 1..19 step 2 x
+    alpha {0.2, 0.3, 0.4, 0.5} at the chosen rank - 11 + 40 fits of tuning_iter = 30 (31 ALS iterations each)."""
+    ranks = list(range(10, 31, 2))
+    lams = [float(v) for v in range(1, 20, 2)]
+    alphas = [0.2, 0.3, 0.4, 0.5]
+    return ranks, lams, alphas
+
+
+def run_tune(args, w, rank, world, local):
+    """tune() grid as REPLICAS: every rank holds the full problem, the points of each phase are dealt round-robin in order of
+    decreasing expected cost; no data-path communication (the RMSE table is gathered with torch.distributed between phases)."""
+    from insider_b200 import _cabi, synth
+
+    dist = Dist(rank, world, local)
+    torch = dist.torch
+    N, P = w["N"], w["P"]
+    pb = synth.ageing_like(N=N, P=P, K=w["K"])
+    tr, te = synth.random_masks(N, P, 0.1, 7)
+    n_rep = max(1, args.replicas_per_gpu)
+    ctxs = [_cabi.Context(local) for _ in range(n_rep)]
+    res0 = ctxs[0].upload(_cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0))
+    residents = [res0] + [_cabi.Resident.share(c, res0) for c in ctxs[1:]]
+    ranks, lams, alphas = tune_grid(w)
+    tuning_iter = args.tune_iters
+
+    def run_phase(phase, points):
+        """points: (K, l1, l2, alpha); this rank runs points[rank::world]; returns the table [n, 2] of (train, test) RMSE."""
+        mine = list(range(rank, len(points), world))
+        facs, optl = [], []
+        for i in mine:
+            K, l1, l2, a = points[i]
+            F0, V0 = synth.init_factors(pb.levels, K, P, seed=1000 * phase + i)
+            facs.append(_cabi.HostFactors(F0, V0, K))
+            o = _cabi.default_options()
+            o.lambda1, o.lambda2, o.alpha, o.tuning, o.global_tol, o.sub_tol, o.max_iter, o.seed = l1, l2, a, 1, 1e-9, 1e-5, tuning_iter, 1
+            optl.append(o)
+        outs, _ = _cabi.tune_batch(residents, facs, optl) if mine else ([], [])
+        tab = np.full((len(points), 4), 0.0)
+        for i, o in zip(mine, outs):
+            tab[i] = (o["train_rmse"], o["test_rmse"], o["loop_ms"], o["iters_run"])
+        return dist.gather_array(tab).sum(axis=0)
+
+    # untimed warm-up: one short fit per distinct kernel family (ridge, elastic net)
+    if args.warmup > 0:
+        for K, a in ((ranks[0], 0.0), (w["K"], 0.4)):
+            F0, V0 = synth.init_factors(pb.levels, K, P, seed=3)
+            o = _cabi.default_options()
+            o.lambda1 = o.lambda2 = 1.0
+            o.alpha, o.tuning, o.max_iter = a, 1, args.warmup
+            res0.optimize(_cabi.HostFactors(F0, V0, K), o)
+    sampler = ClockSampler(local)
+    dist.barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    p1 = [(k, 0.1, 0.1, 0.0) for k in sorted(ranks, reverse=True)]                    # R/insider.R:120-121
+    tab1 = run_phase(0, p1)
+    best = p1[int(np.argmin(tab1[:, 1]))][0]                                          # which.min(test_rmse)  :136
+    p2 = [(best, l, l, a) for a in alphas for l in lams]                              # expand.grid: lambda fastest  :145
+    tab2 = run_phase(1, p2)
+    dist.barrier()
+    secs = dist.reduce(time.perf_counter() - t0)
+    sampler.stop_flag = True
+    if rank == 0:
+        n_fits = len(p1) + len(p2)
+        iters = float(tab1[:, 3].sum() + tab2[:, 3].sum())
+        line = {"metric": "als_iterations_per_second", "value": iters / secs, "unit": "iterations/s", "n_gpus": world, "steps": int(iters),
+                "warmup": args.warmup, "ms_per_step": 1e3 * secs / iters, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "N": N, "P": P, "grid": "K 10..30 step 2 @ (0.1,0.1,0), then lambda 1..19 step 2 x alpha {.2,.3,.4,.5}",
+                           "tuning": 1, "tuning_iter": tuning_iter, "parallelism": f"replicas: grid points round-robin over ranks, {n_rep} context(s) per GPU",
+                           "l2": "no flush: Y (134 MB) exceeds L2"},
+                "grid_seconds": secs, "fits": n_fits, "fits_per_second": n_fits / secs, "chosen_rank": int(best),
+                "device_loop_seconds_sum_over_fits": float((tab1[:, 2].sum() + tab2[:, 2].sum()) * 1e-3),
+                "rank_tuning": [[p[0], float(t[0]), float(t[1])] for p, t in zip(p1, tab1)],
+                "reg_tuning_best": [p2[int(np.argmin(tab2[:, 1]))][1], p2[int(np.argmin(tab2[:, 1]))][3], float(tab2[:, 1].min())],
+                "e2e": {"value": iters / secs, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "what": "wall clock of the whole grid between barriers: factor H2D/D2H of every fit inside, the one upload of Y/masks outside"},
+                "gpu_launches": None, "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    for r in residents[1:]:
+        r.release()
+    res0.release()
+    for c in ctxs:
+        c.close()
+    dist.close()
 
 
 def main():
@@ -319,7 +495,12 @@ def main():
     ap.add_argument("--workload", default="ageing_full_377x44477_K23_fit", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-late", action="store_true", help="skip the steady-state (late iterations) measurement")
+    ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-global_tol legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg")
     ap.add_argument("--late-start", type=int, default=150)
+    ap.add_argument("--ref-genes", type=int, default=0, help="--impl reference: time only the first G genes (default: all)")
+    ap.add_argument("--replicas-per-gpu", type=int, default=1, help="tune workload: concurrent contexts per GPU")
+    ap.add_argument("--tune-iters", type=int, default=30, help="tune workload: tuning_iter")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     w = WORKLOADS[args.workload]
@@ -328,7 +509,10 @@ def main():
         return
     if world != args.gpus and not (world == 1 and args.gpus == 1):
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun --nproc-per-node {args.gpus}", file=sys.stderr)
-    run_ours(args, w, rank, world, local)
+    if args.workload.endswith("_tune"):
+        run_tune(args, w, rank, world, local)
+    else:
+        run_ours(args, w, rank, world, local)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,10 @@
  *                                        exposed iteration-by-iteration for benchmarks and parity tests
  *   insider_b200_strong_cd           <-  .Call(`_insider_strong_coordinate_descent`, 8 SEXPs)
  *                                        src/RcppExports.cpp:34-50 -> src/coordinate_descent.cpp:57-127
+ *   insider_b200_optimize_continuous <-  .Call(`_insider_optimize_continuous_v2`, 8 SEXPs)
+ *                                        src/RcppExports.cpp:69-84 -> optimize_continuous_v2()  src/optimize.cpp:77-137
  *   insider_b200_fit_interaction     <-  fit_interaction()  src/fit_interaction.cpp:10-90 (not exported by the reference)
+ *   insider_b200_glm_interaction     <-  glm_interaction()  R/glm_interaction.R:2-30 (per-level OLS + Gaussian-GLM p-values)
  *   insider_b200_split               <-  ratio_splitter()  R/utils.R:78-117 (bit-exact train/test masks)
  *   insider_b200_tune_batch          <-  the two grid loops of tune()  R/insider.R:100-132, 145-174
  *
@@ -39,7 +42,7 @@
 extern "C" {
 #endif
 
-#define INSIDER_B200_VERSION 100
+#define INSIDER_B200_VERSION 200
 
 enum {
     INSIDER_OK = 0,
@@ -50,7 +53,7 @@ enum {
     INSIDER_ERR_DIVERGED = 5,       /* NaN/Inf loss */
     INSIDER_ERR_EMPTY_TEST_SET = 6, /* tuning=1 with no test entries (reference: arma::mean of empty throws, src/utils.cpp:67) */
     INSIDER_ERR_NOMEM = 7,
-    INSIDER_ERR_UNSUPPORTED = 8     /* e.g. latent_dim > 32 */
+    INSIDER_ERR_UNSUPPORTED = 8     /* latent_dim > 32 (checked before anything is uploaded) */
 };
 
 /* mask element types accepted for train/test indicators */
@@ -64,7 +67,11 @@ enum {
 /* coordinate-visit order of the elastic-net solver (src/coordinate_descent.cpp:89 draws it from R's global RNG,
  * which cannot be reproduced by a parallel solver; see DESIGN.md "permutations") */
 enum {
-    INSIDER_PERM_COUNTER = 1,  /* counter-based: key(seed, als_iter, gene, draw) -> values sorted ascending */
+    INSIDER_PERM_COUNTER = 1,  /* counter-based: key(seed, als_iter, sweep index of the solve) selects one of 4096 precomputed
+                                * randperm-style permutations of the K coordinates; a gene visits its ACTIVE coordinates in that
+                                * order. The gene is deliberately NOT part of the key: every gene at the same sweep index of the
+                                * same ALS iteration shares the order (fresh and uniformly random per sweep, like
+                                * randperm(|inc|), but not independent across genes) - DESIGN.md section 2 "Permutations" */
     INSIDER_PERM_IDENTITY = 2  /* ascending coordinate order */
 };
 
@@ -173,7 +180,9 @@ int64_t insider_b200_als_hint_sweeps(insider_session* s, const int32_t* hint, in
 
 /* batched single-column elastic-net solves (src/coordinate_descent.cpp:57-127). Problem b uses XtX[b] (K x K), Xty[b] (K),
  * wstart[b] (K); X and y of the reference signature are not needed in covariance form and are accepted as NULL.
- * shared_gram != 0: one K x K matrix for all columns. beta: K x n_cols out; sweeps: n_cols out (optional). */
+ * shared_gram != 0: one K x K matrix for all columns. beta: K x n_cols out; sweeps: n_cols out (optional).
+ * gene0 is accepted for source compatibility and IGNORED: the visiting order does not depend on the gene (see
+ * INSIDER_PERM_COUNTER), so results do not depend on which columns of a larger problem a batch holds. */
 int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const double* XtX, int32_t shared_gram, const double* Xty,
                            const double* wstart, double lambda, double alpha, double tol, int32_t perm_mode, uint64_t seed,
                            uint32_t als_iter, uint64_t gene0, double* beta, int32_t* sweeps, char* errbuf, size_t errlen);
@@ -189,11 +198,35 @@ int insider_b200_fit_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t
 int insider_b200_split(const double* data, int64_t N, int64_t P, double ratio, uint32_t seed, int32_t* train, int32_t* test,
                        int32_t* na, int64_t* n_test, char* errbuf, size_t errlen);
 
-/* grid of fits on one resident problem (tune(), R/insider.R:100-174): point g uses K[g], lambda[g] (both lambda1 and
- * lambda2), alpha[g]; factors are initialised by the caller per point (fac[g]); results in res[g]. Points are run
- * back-to-back on this context; across GPUs the caller distributes points over contexts (replicas, no communication). */
-int insider_b200_tune_batch(insider_ctx* ctx, insider_resident* r, int32_t n_points, const insider_factors* fac,
-                            const insider_options* opt, insider_result* res, char* errbuf, size_t errlen);
+/* one continuous covariate's factor (optimize_continuous_v2, src/optimize.cpp:77-137; same 8 arguments as the registered
+ * `_insider_optimize_continuous_v2`, src/RcppExports.cpp:69-84, with `gram` = V V^T recomputed on the device):
+ *   data N x P            the residual WITH this covariate's contribution added back (src/optimize.cpp:344)
+ *   indicator N x P       train mask (mask_kind; ignored when tuning = 0)
+ *   updating_factor K     in/out: the covariate's factor w (one row of cfd_matrices[[C+1]])
+ *   c_factor K x P        column_factor V
+ *   updating_confd N      the covariate x
+ * tuning = 1: cyclic coordinate updates until sum|w_prev - w| < 0.1 (:102-126); tuning = 0: the closed form (:127-131). */
+int insider_b200_optimize_continuous(insider_ctx* ctx, int64_t N, int64_t P, int32_t K, const double* data, int32_t mask_kind,
+                                     const void* indicator, double* updating_factor, const double* c_factor,
+                                     const double* updating_confd, double lambda, int32_t tuning, char* errbuf, size_t errlen);
+
+/* glm_interaction (R/glm_interaction.R:2-30): for every interaction level i, ordinary least squares of the level's residual
+ * rows (all P genes, no mask, no ridge) on t(column_factor) - i.e. glm(response ~ . - 1, gaussian) on the stacked data - and
+ * its coefficient table. coeff, pval: n_levels x K column-major (row i-1 = level i); pval = two-sided t-test with
+ * n_i P - K degrees of freedom and the residual-deviance dispersion, like coef(summary(fit))[,4]. */
+int insider_b200_glm_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t K, const double* residual, int32_t n_levels,
+                                 const int32_t* interaction_indicator, const double* column_factor, double* coeff, double* pval,
+                                 char* errbuf, size_t errlen);
+
+/* grid of fits (tune(), R/insider.R:100-174): point g uses fac[g] (K, caller-initialised factors, in/out) and opt[g]
+ * (lambda1, lambda2, alpha, tuning_iter, ...); results in res[g]. The points are independent fits and run as REPLICAS with no
+ * communication: n_ctx contexts (e.g. one per GPU, or several on one GPU: their kernels overlap), context c holding its own
+ * resident copy residents[c] of the same problem. One host thread per context pulls points from a shared queue (a K = 30 fit
+ * costs several times a K = 10 fit: static partitions would idle). point_ctx (optional, n_points) receives the index of the
+ * context that ran each point. Results do not depend on the schedule. Every context must be a plain single-GPU context. */
+int insider_b200_tune_batch(int32_t n_ctx, insider_ctx* const* ctxs, insider_resident* const* residents, int32_t n_points,
+                            const insider_factors* fac, const insider_options* opt, insider_result* res, int32_t* point_ctx,
+                            char* errbuf, size_t errlen);
 
 #ifdef __cplusplus
 }

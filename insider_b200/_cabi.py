@@ -21,7 +21,7 @@ EXPORTED = [
     "insider_b200_upload", "insider_b200_release", "insider_b200_optimize_resident", "insider_b200_als_begin",
     "insider_b200_als_step", "insider_b200_als_read", "insider_b200_als_end", "insider_b200_als_profile", "insider_b200_als_sweeps", "insider_b200_als_hint_sweeps",
     "insider_b200_set_profile", "insider_b200_strong_cd", "insider_b200_fit_interaction", "insider_b200_split",
-    "insider_b200_tune_batch",
+    "insider_b200_tune_batch", "insider_b200_optimize_continuous", "insider_b200_glm_interaction",
 ]
 
 
@@ -64,6 +64,46 @@ class Result(C.Structure):
 _lib = None
 
 
+def _declare(L):
+    """argtypes / restype of every entry point of include/insider_b200.h (without them ctypes passes Python ints as 32-bit
+    C ints, which is wrong for size_t / int64_t arguments that travel on the stack)."""
+    vp, i32, i64, u32, u64, dbl, sz, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double, C.c_size_t, C.c_char_p
+    P = C.POINTER
+    err = (cp, sz)
+    sig = {
+        "insider_b200_default_options": (None, (P(Options),)),
+        "insider_b200_version": (C.c_int, ()),
+        "insider_b200_ctx_create": (C.c_int, (P(vp), C.c_int) + err),
+        "insider_b200_nccl_unique_id": (C.c_int, (vp,) + err),
+        "insider_b200_ctx_create_dist": (C.c_int, (P(vp), C.c_int, C.c_int, C.c_int, vp) + err),
+        "insider_b200_ctx_destroy": (None, (vp,)),
+        "insider_b200_ctx_stream": (vp, (vp,)),
+        "insider_b200_optimize": (C.c_int, (vp, P(Problem), P(Factors), P(Options), P(Result)) + err),
+        "insider_b200_upload": (C.c_int, (vp, P(Problem), P(vp)) + err),
+        "insider_b200_release": (None, (vp,)),
+        "insider_b200_optimize_resident": (C.c_int, (vp, vp, P(Factors), P(Options), P(Result)) + err),
+        "insider_b200_als_begin": (C.c_int, (vp, vp, P(Factors), P(Options), P(vp)) + err),
+        "insider_b200_als_step": (C.c_int, (vp, u32, P(i32), P(dbl)) + err),
+        "insider_b200_als_read": (C.c_int, (vp, P(Factors)) + err),
+        "insider_b200_als_end": (C.c_int, (vp, P(Factors), P(Result)) + err),
+        "insider_b200_als_profile": (C.c_int, (vp, cp, sz, P(dbl), P(i64), C.c_int)),
+        "insider_b200_set_profile": (None, (vp, C.c_int)),
+        "insider_b200_als_sweeps": (i64, (vp, P(i32), i64)),
+        "insider_b200_als_hint_sweeps": (i64, (vp, P(i32), i64)),
+        "insider_b200_strong_cd": (C.c_int, (vp, i32, i64, vp, i32, vp, vp, dbl, dbl, dbl, i32, u64, u32, u64, vp, vp) + err),
+        "insider_b200_fit_interaction": (C.c_int, (vp, i64, i64, i32, vp, i32, vp, vp, i32, vp, vp, i32) + err),
+        "insider_b200_split": (C.c_int, (vp, i64, i64, dbl, u32, vp, vp, vp, P(i64)) + err),
+        "insider_b200_tune_batch": (C.c_int, (i32, P(vp), P(vp), i32, P(Factors), P(Options), P(Result), P(i32)) + err),
+        "insider_b200_optimize_continuous": (C.c_int, (vp, i64, i64, i32, vp, i32, vp, vp, vp, vp, dbl, i32) + err),
+        "insider_b200_glm_interaction": (C.c_int, (vp, i64, i64, i32, vp, i32, vp, vp, vp, vp) + err),
+    }
+    assert sorted(sig) == sorted(EXPORTED)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+
 def lib() -> C.CDLL:
     """Loads the CUDA library; raises if it has not been built (there is no fallback)."""
     global _lib
@@ -73,11 +113,7 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         for name in EXPORTED:
             getattr(L, name)
-        L.insider_b200_ctx_stream.restype = C.c_void_p
-        L.insider_b200_default_options.restype = None
-        L.insider_b200_ctx_destroy.restype = None
-        L.insider_b200_release.restype = None
-        L.insider_b200_set_profile.restype = None
+        _declare(L)
         _lib = L
     return _lib
 
@@ -123,6 +159,16 @@ class HostProblem:
             self.test = np.asfortranarray(test, dtype=dt)
         else:
             self.train = self.test = None
+        # shapes are the caller's contract in C (plain pointers): check them here, where they are still known
+        if self.levels.shape[0] != N:
+            raise ValueError(f"levels has {self.levels.shape[0]} rows, data has {N}")
+        if self.X is not None and self.X.shape[0] != N:
+            raise ValueError(f"ctns_confounder has {self.X.shape[0]} rows, data has {N}")
+        for name, m in (("train_indicator", self.train), ("test_indicator", self.test)):
+            if m is not None and m.shape != (N, P):
+                raise ValueError(f"{name} is {m.shape[0]} x {m.shape[1]} but data is {N} x {P} (ratio_splitter(rm.na.col = TRUE) drops "
+                                 "all-zero columns from the indicators only: drop them from data too)")
+        self.N, self.P = N, P
         p = Problem()
         p.N, p.P, p.C = N, P, self.levels.shape[1]
         p.Q = self.X.shape[1] if self.X is not None else 0
@@ -143,6 +189,12 @@ class HostFactors:
         self.factors = [np.array(f, dtype=np.float64, order="F", copy=True) for f in cfd_factors]
         self.V = np.array(column_factor, dtype=np.float64, order="F", copy=True)
         n = len(self.factors)
+        K = int(K)
+        if self.V.ndim != 2 or self.V.shape[0] != K:
+            raise ValueError(f"column_factor must be latent_dim x P = {K} x P, got {self.V.shape}")
+        for i, f in enumerate(self.factors):
+            if f.ndim != 2 or f.shape[1] != K:
+                raise ValueError(f"cfd_factors[{i}] must have latent_dim = {K} columns, got {f.shape}")
         self._ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in self.factors])
         self._rows = (C.c_int32 * n)(*[f.shape[0] for f in self.factors])
         s = Factors()
@@ -244,13 +296,84 @@ class Context:
         return out
 
 
+    def optimize_continuous(self, data, indicator, updating_factor, c_factor, updating_confd, lam, tuning):
+        """optimize_continuous_v2 (src/optimize.cpp:77-137): returns the updated factor row (K,)."""
+        Y = np.asfortranarray(data, dtype=np.float64)
+        N, P = Y.shape
+        V = np.asfortranarray(c_factor, dtype=np.float64)
+        K = V.shape[0]
+        w = np.array(updating_factor, dtype=np.float64).reshape(-1).copy()
+        x = np.ascontiguousarray(updating_confd, dtype=np.float64).reshape(-1)
+        if V.shape[1] != P or w.size != K or x.size != N:
+            raise ValueError("optimize_continuous: shapes must be data N x P, c_factor K x P, updating_factor K, updating_confd N")
+        ind = None
+        if indicator is not None:
+            ind = np.asfortranarray(indicator, dtype=indicator.dtype if indicator.dtype in (np.int32, np.uint8, np.float64) else np.int32)
+            if ind.shape != (N, P):
+                raise ValueError("optimize_continuous: indicator must be N x P")
+        e = _err()
+        _chk(lib().insider_b200_optimize_continuous(self.h, N, P, K, Y.ctypes.data, mask_kind_of(ind), ind.ctypes.data if ind is not None else None,
+                                                    w.ctypes.data, V.ctypes.data, x.ctypes.data, float(lam), int(tuning), e, len(e)), e)
+        return w
+
+    def glm_interaction(self, residual, interaction_indicator, column_factor):
+        """glm_interaction (R/glm_interaction.R:2-30): returns (coeff_matrix, pval_matrix), each n_levels x K."""
+        R = np.asfortranarray(residual, dtype=np.float64)
+        N, P = R.shape
+        V = np.asfortranarray(column_factor, dtype=np.float64)
+        K = V.shape[0]
+        z = np.ascontiguousarray(interaction_indicator, dtype=np.int32).reshape(-1)
+        if V.shape[1] != P or z.size != N:
+            raise ValueError("glm_interaction: shapes must be residual N x P, column_factor K x P, interaction_indicator N")
+        L = int(z.max())
+        coeff = np.zeros((L, K), order="F")
+        pval = np.zeros((L, K), order="F")
+        e = _err()
+        _chk(lib().insider_b200_glm_interaction(self.h, N, P, K, R.ctypes.data, L, z.ctypes.data, V.ctypes.data, coeff.ctypes.data, pval.ctypes.data,
+                                                e, len(e)), e)
+        return coeff, pval
+
+
+def tune_batch(residents, facs, opts):
+    """insider_b200_tune_batch: the grid points (facs[i], opts[i]) as replicas over the contexts of `residents` (one resident copy of
+    the same problem per context). Returns (list of result dicts, context index that ran each point)."""
+    n_ctx, n = len(residents), len(facs)
+    ctxs = (C.c_void_p * n_ctx)(*[r.ctx.h for r in residents])
+    ress = (C.c_void_p * n_ctx)(*[r.h for r in residents])
+    F = (Factors * n)(*[f.struct for f in facs])
+    O = (Options * n)(*opts)
+    R = (Result * n)()
+    bufs = []
+    for i in range(n):
+        mc = int(opts[i].max_iter) // max(1, int(opts[i].check_every) or 10) + 3
+        buf = (Check * mc)()
+        R[i].checks = C.cast(buf, C.POINTER(Check))
+        R[i].max_checks = mc
+        bufs.append(buf)
+    who = (C.c_int32 * max(1, n))()
+    e = _err()
+    _chk(lib().insider_b200_tune_batch(n_ctx, ctxs, ress, n, F, O, R, who, e, len(e)), e)
+    return [result_dict(R[i], bufs[i]) for i in range(n)], [int(who[i]) for i in range(n)]
+
+
 class Resident:
     def __init__(self, ctx: Context, prob: HostProblem):
         self.ctx = ctx
         self.prob = prob
         self.h = C.c_void_p()
+        self.owner = True
         e = _err()
         _chk(lib().insider_b200_upload(ctx.h, C.byref(prob.struct), C.byref(self.h), e, len(e)), e)
+
+    @classmethod
+    def share(cls, ctx: Context, other: "Resident") -> "Resident":
+        """The same device-resident problem seen from another context ON THE SAME DEVICE (a resident problem is read-only
+        after upload): several contexts = several streams whose fits overlap (tune() replicas on one GPU). Not an owner."""
+        if ctx.device != other.ctx.device or ctx.world != 1:
+            raise ValueError("a resident problem can only be shared between single-GPU contexts on the same device")
+        r = cls.__new__(cls)
+        r.ctx, r.prob, r.h, r.owner = ctx, other.prob, other.h, False
+        return r
 
     def optimize(self, fac: HostFactors, opt: Options) -> dict:
         r, buf = make_result(int(opt.max_iter) // max(1, int(opt.check_every) or 10) + 3)
@@ -262,9 +385,9 @@ class Resident:
         return Session(self, fac, opt)
 
     def release(self):
-        if self.h:
+        if self.h and self.owner:
             lib().insider_b200_release(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -303,14 +426,12 @@ class Session:
     def sweeps(self, n: int) -> np.ndarray:
         """Per-gene coordinate-descent sweep counts of the last iteration (dense elastic-net path; diagnostics)."""
         out = np.zeros(n, dtype=np.int32)
-        lib().insider_b200_als_sweeps.restype = C.c_int64
         got = lib().insider_b200_als_sweeps(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(n))
         return out[:got]
 
     def hint_sweeps(self, hint) -> int:
         """Expected sweep counts of the next iteration (orders the dense solver's work; results do not depend on it)."""
         h = np.ascontiguousarray(hint, dtype=np.int32)
-        lib().insider_b200_als_hint_sweeps.restype = C.c_int64
         return int(lib().insider_b200_als_hint_sweeps(self.h, h.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(h.size)))
 
     def end(self, read_factors: bool = True) -> dict:

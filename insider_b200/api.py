@@ -150,7 +150,7 @@ def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None
     """reference R/insider.R:81-176. Returns dict(rank_tuning, latent_rank, reg_tuning).
 
     Grid points are independent fits. With ``ctxs`` (a list of contexts, e.g. one per GPU) the points of each phase are
-    run as replicas, one host thread per context, every context holding its own resident copy of the data — no
+    run as replicas by insider_b200_tune_batch, every context holding its own resident copy of the data — no
     communication. Each point draws its initial factors from a generator seeded by (seed, phase, point index), so the
     results do not depend on how points are scheduled (the reference uses whatever R's RNG stream holds at that moment).
     """
@@ -166,21 +166,20 @@ def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None
     residents = [_resident_for(obj, c) for c in ctx_list]       # all fits of a context share one upload
 
     def run_points(phase, points):
-        """points: list of (K, lambda1, lambda2, alpha); returns the fitted dicts in order."""
-        out = [None] * len(points)
-
-        def work(slot):
-            for i in range(slot, len(points), len(ctx_list)):
-                K, l1, l2, a = points[i]
-                flist, V = _init_factors(obj, int(K), np.random.default_rng([seed, phase, i]))
-                out[i] = optimize(None, flist, V, None, None, None, None, obj["inc_continuous"], int(K), l1, l2, a, 1, p["global_tol"],
-                                  p["sub_tol"], p["tuning_iter"], seed=seed, ctx=ctx_list[slot], resident=residents[slot])
-        if len(ctx_list) == 1:
-            work(0)
-        else:
-            import concurrent.futures as cf
-            with cf.ThreadPoolExecutor(len(ctx_list)) as ex:
-                list(ex.map(work, range(len(ctx_list))))
+        """points: list of (K, lambda1, lambda2, alpha); returns the fitted dicts in order. One insider_b200_tune_batch call:
+        the library spreads the points over the contexts (one host thread per context, shared queue)."""
+        facs, opts = [], []
+        for i, (K, l1, l2, a) in enumerate(points):
+            flist, V = _init_factors(obj, int(K), np.random.default_rng([seed, phase, i]))
+            facs.append(_cabi.HostFactors(flist, V, int(K)))
+            o = _cabi.default_options()
+            o.lambda1, o.lambda2, o.alpha, o.tuning = float(l1), float(l2), float(a), 1
+            o.global_tol, o.sub_tol, o.max_iter, o.seed = float(p["global_tol"]), float(p["sub_tol"]), int(p["tuning_iter"]), int(seed)
+            opts.append(o)
+        out, _ = _cabi.tune_batch(residents, facs, opts)
+        for f, o in zip(facs, out):
+            o["row_matrices"] = {f"factor{i}": m for i, m in enumerate(f.factors)}
+            o["column_factor"] = f.V
         return out
 
     rank_tuning, reg_tuning = None, None
@@ -230,3 +229,32 @@ def fit(obj, latent_dimension=None, lambda_=None, alpha=None, partition=0, *, se
     obj["test_rmse"] = fitted["test_rmse"]
     obj["fit_info"] = {k: fitted[k] for k in ("train_rmse", "loss", "iters_run", "checks", "cd_sweeps", "loop_ms")}
     return obj
+
+
+def strong_coordinate_descent(X, y, wstart, lambda_, alpha, XtX, Xty, tol, *, seed=0, ctx=None):
+    """reference R/RcppExports.R:8-10 -> src/coordinate_descent.cpp:57-127, same 8 arguments (X and y are not needed in
+    covariance form and may be None). Returns beta (K,)."""
+    ctx = ctx or default_context()
+    beta, _ = ctx.strong_cd(np.asarray(XtX, dtype=np.float64), np.asarray(Xty, dtype=np.float64).reshape(-1), np.asarray(wstart, dtype=np.float64).reshape(-1),
+                            float(lambda_), float(alpha), tol=float(tol), seed=seed)
+    return beta[:, 0]
+
+
+def optimize_continuous_v2(data, indicator, updating_factor, c_factor, updating_confd, gram, lambda_, tuning, *, ctx=None):
+    """reference R/RcppExports.R:16-18 -> src/optimize.cpp:77-137, same 8 arguments; `updating_factor` is updated in place
+    like the reference's `rowvec&` (and returned). `gram` is accepted for signature compatibility: V V' is recomputed."""
+    ctx = ctx or default_context()
+    if tuning not in (0, 1):
+        raise ValueError("Parameter tuning should be either 0 or 1!")
+    w = ctx.optimize_continuous(data, indicator if tuning == 1 else None, updating_factor, c_factor, updating_confd, lambda_, tuning)
+    if isinstance(updating_factor, np.ndarray) and updating_factor.size == w.size:
+        updating_factor.reshape(-1)[...] = w
+    return w
+
+
+def glm_interaction(residual, train_indicator, interaction_indicator, column_factor, tol=1e-10, n_cores=10, *, ctx=None):
+    """reference R/glm_interaction.R:2-30: list(coeff_matrix, pval_matrix). Like the reference, train_indicator, tol and n_cores
+    are accepted and unused (the regression runs on every entry of the residual rows)."""
+    ctx = ctx or default_context()
+    coeff, pval = ctx.glm_interaction(residual, interaction_indicator, column_factor)
+    return [coeff, pval]

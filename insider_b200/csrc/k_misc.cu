@@ -111,6 +111,22 @@ __global__ void __launch_bounds__(256) k_check(CheckState* st, const double* __r
 
 __global__ void k_bump_iter(CheckState* st) { st->als_iter += 1; }
 
+// part[block][i] = sum over the block's genes of Y[j][i]^2 (threads along rows: coalesced); a fixed-order reduce follows
+__global__ void __launch_bounds__(256) k_row_sumsq(const double* __restrict__ Y, int N, int ldY, int64_t P, double* __restrict__ part) {
+    const int64_t per = (P + gridDim.x - 1) / gridDim.x;
+    const int64_t j0 = (int64_t)blockIdx.x * per, j1 = (j0 + per < P) ? j0 + per : P;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int64_t j = j0;
+        for (; j + 4 <= j1; j += 4) {
+            const double a = Y[j * ldY + i], b = Y[(j + 1) * ldY + i], c = Y[(j + 2) * ldY + i], d = Y[(j + 3) * ldY + i];
+            s0 = fma(a, a, s0); s1 = fma(b, b, s1); s2 = fma(c, c, s2); s3 = fma(d, d, s3);
+        }
+        for (; j < j1; ++j) { const double a = Y[j * ldY + i]; s0 = fma(a, a, s0); }
+        part[(size_t)blockIdx.x * N + i] = (s0 + s1) + (s2 + s3);
+    }
+}
+
 }  // namespace
 
 void launch_pack_mask(const void* src, int kind, int64_t N, int64_t n_genes, int Wp, uint32_t* dstC, cudaStream_t st) {
@@ -147,5 +163,9 @@ void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initi
 }
 
 void launch_bump_iter(CheckState* state, cudaStream_t st) { k_bump_iter<<<1, 1, 0, st>>>(state); }
+
+void launch_row_sumsq(const Geom& g, const double* Y, double* part, int n_blocks, cudaStream_t st) {
+    if (g.P > 0) k_row_sumsq<<<n_blocks, 256, 0, st>>>(Y, g.N, g.ldY, g.P, part);
+}
 
 }  // namespace ib

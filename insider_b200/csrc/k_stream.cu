@@ -623,14 +623,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
+// The opt-in is a per-device function attribute: no caching here (a context on another device must opt in again and
+// the call is cheap next to a kernel launch).
 template <typename KernelT>
 void set_smem(KernelT k, size_t bytes) {
-    static thread_local const void* last = nullptr;
-    static thread_local size_t last_bytes = 0;
-    if (last != (const void*)k || last_bytes < bytes) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        last = (const void*)k; last_bytes = bytes;
-    }
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 StreamArgs base_args(const Geom& g) {

@@ -160,5 +160,7 @@ void launch_sse_reduce(const double* partial, int n_blocks, CheckState* state, c
 // row_reg = lambda1 * sum ||A_c||^2 (+ W); then loss, delta, decay ladder, convergence (src/optimize.cpp:381-408)
 void launch_check(CheckState* state, const double* A_all, int64_t n_A, int initial, int iter, void* record_out, cudaStream_t st);
 void launch_bump_iter(CheckState* state, cudaStream_t st);
+// part[n_blocks][N]: per-row sums of squares of Y over each block's genes (glm_interaction's residual sums of squares)
+void launch_row_sumsq(const Geom& g, const double* Y, double* part, int n_blocks, cudaStream_t st);
 
 }  // namespace ib

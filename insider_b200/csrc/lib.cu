@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -15,7 +16,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/insider_b200.h"
@@ -544,9 +547,10 @@ void run_iteration(insider_session* s) {
 
 insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_factors* f, const insider_options* o) {
     REQUIRE(r && f && o, "null argument");
-    REQUIRE(r->ctx == ctx, "resident problem belongs to another context");
+    // a resident problem is read-only after upload: contexts on the same device may share it (tune() replicas on one GPU)
+    REQUIRE(r->ctx == ctx || (r->ctx->device == ctx->device && r->ctx->world == 1 && ctx->world == 1), "resident problem belongs to a context on another device");
     REQUIRE(o->tuning == 0 || o->tuning == 1, "Parameter tuning should be either 0 or 1!");
-    if (f->K < 1 || f->K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "latent_dim must be in 1..32"};
+    if (f->K < 1 || f->K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "latent_dim = " + std::to_string(f->K) + " is not supported: libinsider_b200 handles latent_dim 1..32"};
     REQUIRE(f->n_factors == r->C + r->inc_continuous, "n_factors must equal C + inc_continuous");
     REQUIRE(f->factors && f->factor_rows && f->column_factor, "factor buffers required");
     REQUIRE(o->tuning == 0 || r->has_masks, "tuning = 1 needs train/test masks");
@@ -913,6 +917,10 @@ int insider_b200_optimize_resident(insider_ctx* ctx, insider_resident* r, const 
 int insider_b200_optimize(insider_ctx* ctx, const insider_problem* prob, const insider_factors* fac, const insider_options* opt, insider_result* res,
                           char* errbuf, size_t errlen) {
     insider_resident* r = nullptr;
+    if (fac && (fac->K < 1 || fac->K > KMAX)) {                         // before anything is uploaded
+        set_err(errbuf, errlen, "latent_dim = %d is not supported: libinsider_b200 handles latent_dim 1..%d", fac->K, KMAX);
+        return INSIDER_ERR_UNSUPPORTED;
+    }
     const bool trace = getenv("INSIDER_B200_TRACE") != nullptr;         // phase wall times of the one-shot call on stderr
     const auto t0 = std::chrono::steady_clock::now();
     int rc = insider_b200_upload(ctx, prob, &r, errbuf, errlen);
@@ -932,14 +940,80 @@ int insider_b200_optimize(insider_ctx* ctx, const insider_problem* prob, const i
     return rc;
 }
 
-int insider_b200_tune_batch(insider_ctx* ctx, insider_resident* r, int32_t n_points, const insider_factors* fac, const insider_options* opt,
-                            insider_result* res, char* errbuf, size_t errlen) {
-    if (!fac || !opt || !res || n_points < 0) { set_err(errbuf, errlen, "null argument"); return INSIDER_ERR_INVALID_ARG; }
-    for (int i = 0; i < n_points; ++i) {
-        int rc = insider_b200_optimize_resident(ctx, r, &fac[i], &opt[i], &res[i], errbuf, errlen);
-        if (rc) return rc;
+int insider_b200_tune_batch(int32_t n_ctx, insider_ctx* const* ctxs, insider_resident* const* residents, int32_t n_points, const insider_factors* fac,
+                            const insider_options* opt, insider_result* res, int32_t* point_ctx, char* errbuf, size_t errlen) {
+    if (n_ctx < 1 || !ctxs || !residents || !fac || !opt || !res || n_points < 0) { set_err(errbuf, errlen, "null argument"); return INSIDER_ERR_INVALID_ARG; }
+    for (int c = 0; c < n_ctx; ++c)
+        if (!ctxs[c] || !residents[c] || ctxs[c]->world != 1) { set_err(errbuf, errlen, "tune_batch needs plain single-GPU contexts, one resident problem each"); return INSIDER_ERR_INVALID_ARG; }
+    // replicas: one host thread per context pulls grid points from a shared counter (no communication between fits)
+    std::atomic<int> next{0};
+    std::atomic<int> first_rc{INSIDER_OK};
+    std::mutex err_mu;
+    std::string err_msg;
+    auto worker = [&](int c) {
+        char local[512];
+        while (first_rc.load() == INSIDER_OK) {
+            const int i = next.fetch_add(1);
+            if (i >= n_points) break;
+            local[0] = 0;
+            const int rc = insider_b200_optimize_resident(ctxs[c], residents[c], &fac[i], &opt[i], &res[i], local, sizeof local);
+            if (point_ctx) point_ctx[i] = c;
+            if (rc != INSIDER_OK) {
+                int expected = INSIDER_OK;
+                if (first_rc.compare_exchange_strong(expected, rc)) { std::lock_guard<std::mutex> lk(err_mu); err_msg = "grid point " + std::to_string(i) + ": " + local; }
+            }
+        }
+    };
+    if (n_ctx == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int c = 0; c < n_ctx; ++c) th.emplace_back(worker, c);
+        for (auto& t : th) t.join();
     }
-    return INSIDER_OK;
+    if (first_rc.load() != INSIDER_OK) set_err(errbuf, errlen, "%s", err_msg.c_str());
+    return first_rc.load();
+}
+
+int insider_b200_optimize_continuous(insider_ctx* ctx, int64_t N, int64_t P, int32_t K, const double* data, int32_t mask_kind, const void* indicator,
+                                     double* updating_factor, const double* c_factor, const double* updating_confd, double lambda, int32_t tuning,
+                                     char* errbuf, size_t errlen) {
+    // The problem "one continuous covariate, nothing else": row factor u_k = x_k w. Statistics B, G (, D) of `data`, then the
+    // K x K update of k_cont_partial / k_cont_final - the same launches the continuous block of a full fit runs (run_iteration).
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(ctx && data && updating_factor && c_factor && updating_confd, "null argument");
+        REQUIRE(tuning == 0 || tuning == 1, "Parameter tuning should be either 0 or 1!");            // src/optimize.cpp:133-135
+        REQUIRE(tuning == 0 || (indicator && mask_kind != INSIDER_MASK_NONE), "tuning = 1 needs the indicator matrix");
+        REQUIRE(ctx->world == 1, "optimize_continuous runs on a single-GPU context");
+        if (K < 1 || K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "latent_dim must be in 1..32"};
+        insider_problem pb{};
+        pb.N = N; pb.P = P; pb.C = 0; pb.Q = 1; pb.inc_continuous = 1; pb.Y = data; pb.X = updating_confd;
+        pb.mask_kind = tuning == 1 ? mask_kind : INSIDER_MASK_NONE; pb.train = indicator; pb.test = indicator;
+        std::unique_ptr<insider_resident, void (*)(insider_resident*)> r(do_upload(ctx, &pb), insider_b200_release);
+        std::vector<double> V((size_t)K * P);
+        memcpy(V.data(), c_factor, V.size() * 8);
+        double* fp[1] = {updating_factor}; int32_t rows[1] = {1};
+        insider_factors f{K, 1, fp, rows, V.data()};
+        insider_options o; insider_b200_default_options(&o);
+        o.tuning = tuning; o.lambda1 = lambda; o.max_iter = 0;
+        insider_session* s = do_begin(ctx, r.get(), &f, &o);
+        try {
+            cudaStream_t st = ctx->stream;
+            const Geom& g = s->g; const int KK = g.KP * g.KP;
+            launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st);
+            if (s->masked) launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st);
+            double* outs[3] = {s->B, s->G, s->D};
+            const double* parts[3] = {s->Bp, s->Gp, s->Dp};
+            const int64_t ns[3] = {(int64_t)g.N * g.KP, KK, (int64_t)g.N * KK};
+            const int nps[3] = {s->rb_splits, s->rb_splits * ROW_B_GRAM_PARTS, s->d_splits};
+            launch_reduce_jobs(s->masked ? 3 : 2, outs, parts, ns, nps, st);
+            launch_continuous(g, s->masked, r->X, s->A_all, s->B, s->G, s->D, lambda, s->U, s->cont_scratch, s->err_dev, st);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            download_factors(s, &f);
+            int err = 0; CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));
+            if (err) throw Err{INSIDER_ERR_NOT_SPD, "continuous-covariate normal equations not positive definite"};
+        } catch (...) { destroy_session(s); throw; }
+        destroy_session(s);
+    });
 }
 
 int insider_b200_strong_cd(insider_ctx* ctx, int32_t K, int64_t n_cols, const double* XtX, int32_t shared_gram, const double* Xty, const double* wstart,
@@ -1015,6 +1089,144 @@ int insider_b200_fit_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t
         } catch (...) { destroy_session(s); throw; }
         destroy_session(s);
         memcpy(interactions, A0.data(), A0.size() * 8);
+    });
+}
+
+namespace {
+// regularised incomplete beta I_x(a, b) by the continued fraction (modified Lentz); lx = log(x), lxc = log(1 - x) are passed
+// in because x = df / (df + t^2) is within rounding of 1 for the large degrees of freedom this is used with
+double betacf(double a, double b, double x) {
+    const double tiny = 1e-300, eps = 1e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 2000000; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d; h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < eps) break;
+    }
+    return h;
+}
+// two-sided p-value of Student's t with df degrees of freedom: I_{df/(df+t^2)}(df/2, 1/2)   (R: 2 * pt(-|t|, df))
+double student_two_sided(double t, double df) {
+    if (!(df > 0.0) || std::isnan(t)) return std::nan("");
+    const double t2 = t * t;
+    if (t2 == 0.0) return 1.0;
+    if (std::isinf(t2)) return 0.0;
+    const double a = 0.5 * df, b = 0.5;
+    const double x = df / (df + t2), xc = t2 / (df + t2);
+    const double lx = -log1p(t2 / df), lxc = log(xc);
+    const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * lx + b * lxc);
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
+    return 1.0 - bt * betacf(b, a, xc) / b;
+}
+}  // namespace
+
+int insider_b200_glm_interaction(insider_ctx* ctx, int64_t N, int64_t P, int32_t K, const double* residual, int32_t n_levels,
+                                 const int32_t* interaction_indicator, const double* column_factor, double* coeff, double* pval, char* errbuf,
+                                 size_t errlen) {
+    // Per level i the stacked regression of R/glm_interaction.R:15-24 has X'X = n_i V V' and X'y = V sum_{k in i} r_k: the dense
+    // row update with lambda = 0 (the same launches as insider_b200_fit_interaction, tuning = 0). The coefficient table needs, per
+    // level, RSS = sum_k |r_k|^2 - 2 a' X'y + n_i a' G a (k_row_sumsq gives the first term) and diag((n_i G)^-1).
+    return guarded(errbuf, errlen, [&] {
+        REQUIRE(ctx && residual && interaction_indicator && column_factor && coeff && pval, "null argument");
+        REQUIRE(ctx->world == 1, "glm_interaction runs on a single-GPU context");
+        if (K < 1 || K > KMAX) throw Err{INSIDER_ERR_UNSUPPORTED, "latent_dim must be in 1..32"};
+        insider_problem pb{};
+        pb.N = N; pb.P = P; pb.C = 1; pb.Q = 0; pb.inc_continuous = 0; pb.Y = residual; pb.levels = interaction_indicator; pb.mask_kind = INSIDER_MASK_NONE;
+        std::unique_ptr<insider_resident, void (*)(insider_resident*)> r(do_upload(ctx, &pb), insider_b200_release);
+        REQUIRE(r->L[0] == n_levels, "n_levels must equal the number of interaction levels");
+        std::vector<double> A0((size_t)n_levels * K, 0.0), V((size_t)K * P);
+        memcpy(V.data(), column_factor, V.size() * 8);
+        double* fp[1] = {A0.data()}; int32_t rows[1] = {n_levels};
+        insider_factors f{K, 1, fp, rows, V.data()};
+        insider_options o; insider_b200_default_options(&o);
+        o.tuning = 0; o.lambda1 = 0.0; o.max_iter = 0;
+        insider_session* s = do_begin(ctx, r.get(), &f, &o);
+        try {
+            cudaStream_t st = ctx->stream;
+            const Geom& g = s->g; const int KP = g.KP, KK = KP * KP, Nn = g.N;
+            const int nb = std::max(1, std::min<int>(ctx->sm_count, (int)std::min<int64_t>(g.P, 1 << 20)));
+            double* ss_part = s->pool.get<double>((size_t)nb * Nn, true, st);
+            double* ss = s->pool.get<double>((size_t)Nn, true, st);
+            launch_row_b(g, false, r->Y, nullptr, s->V, s->Bp, s->Gp, s->rb_splits, st);
+            launch_reduce_partials(s->G, s->Gp, KK, s->rb_splits * ROW_B_GRAM_PARTS, st);
+            launch_reduce_partials(s->B, s->Bp, (int64_t)Nn * KP, s->rb_splits, st);
+            launch_row_sumsq(g, r->Y, ss_part, nb, st);
+            launch_reduce_partials(ss, ss_part, Nn, nb, st);
+            launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, 0.0, s->Lfac, s->err_dev, st);
+            launch_level_update(g, false, s->designs[0], 0, s->G, s->B, s->T, s->Lfac, s->U, st);
+            std::vector<double> Bh((size_t)Nn * KP), Gh(KK), ssh(Nn);
+            CUDA_TRY(cudaMemcpyAsync(Bh.data(), s->B, Bh.size() * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(Gh.data(), s->G, Gh.size() * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ssh.data(), ss, ssh.size() * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            download_factors(s, &f);
+            int err = 0; CUDA_TRY(cudaMemcpy(&err, s->err_dev, 4, cudaMemcpyDeviceToHost));
+            if (err) throw Err{INSIDER_ERR_NOT_SPD, "V V' is not positive definite: the regression of glm_interaction is rank deficient"};
+            // K x K host algebra of summary.glm: diag(G^-1) by Cholesky
+            std::vector<double> Lc((size_t)K * K, 0.0), ginv_diag(K, 0.0);
+            for (int j = 0; j < K; ++j) {
+                double d = Gh[(size_t)j * KP + j];
+                for (int m = 0; m < j; ++m) d -= Lc[(size_t)j * K + m] * Lc[(size_t)j * K + m];
+                if (!(d > 0.0)) throw Err{INSIDER_ERR_NOT_SPD, "V V' is not positive definite"};
+                Lc[(size_t)j * K + j] = sqrt(d);
+                for (int i = j + 1; i < K; ++i) {
+                    double v = Gh[(size_t)i * KP + j];
+                    for (int m = 0; m < j; ++m) v -= Lc[(size_t)i * K + m] * Lc[(size_t)j * K + m];
+                    Lc[(size_t)i * K + j] = v / Lc[(size_t)j * K + j];
+                }
+            }
+            for (int c = 0; c < K; ++c) {                       // column c of L^-1, then (G^-1)_cc = sum_i (L^-1)_ic^2 ... via solve
+                std::vector<double> y(K, 0.0);
+                for (int i = c; i < K; ++i) {
+                    double v = (i == c) ? 1.0 : 0.0;
+                    for (int m = c; m < i; ++m) v -= Lc[(size_t)i * K + m] * y[m];
+                    y[i] = v / Lc[(size_t)i * K + i];
+                }
+                double acc = 0.0;
+                for (int i = c; i < K; ++i) acc += y[i] * y[i];
+                ginv_diag[c] = acc;
+            }
+            const std::vector<int>& lor = r->lor_host[0];
+            std::vector<double> SB((size_t)n_levels * K, 0.0), SS(n_levels, 0.0), cnt(n_levels, 0.0);
+            for (int k = 0; k < Nn; ++k) {
+                const int l = lor[k];
+                for (int a = 0; a < K; ++a) SB[(size_t)l * K + a] += Bh[(size_t)k * KP + a];
+                SS[l] += ssh[k]; cnt[l] += 1.0;
+            }
+            for (int l = 0; l < n_levels; ++l) {
+                double aSB = 0.0, aGa = 0.0;
+                for (int a = 0; a < K; ++a) {
+                    const double ca = A0[l + (size_t)a * n_levels];
+                    aSB += ca * SB[(size_t)l * K + a];
+                    double ga = 0.0;
+                    for (int b = 0; b < K; ++b) ga += Gh[(size_t)a * KP + b] * A0[l + (size_t)b * n_levels];
+                    aGa += ca * ga;
+                }
+                const double rss = SS[l] - 2.0 * aSB + cnt[l] * aGa;
+                const double df = cnt[l] * (double)P - (double)K;
+                const double sigma2 = rss / df;                                    // dispersion of the gaussian family (summary.glm)
+                for (int a = 0; a < K; ++a) {
+                    const double ca = A0[l + (size_t)a * n_levels];
+                    const double se = sqrt(sigma2 * ginv_diag[a] / cnt[l]);
+                    coeff[l + (size_t)a * n_levels] = ca;
+                    pval[l + (size_t)a * n_levels] = student_two_sided(ca / se, df);
+                }
+            }
+        } catch (...) { destroy_session(s); throw; }
+        destroy_session(s);
     });
 }
 

@@ -750,6 +750,31 @@ int oracle_fit_interaction(int N, int P, int K, const double* residual, const in
     return err;
 }
 
+// src/optimize.cpp:77-137 — stand-alone entry with the reference's 8 arguments (`_insider_optimize_continuous_v2`,
+// src/RcppExports.cpp:69-84). data/indicator N x P column-major, w (K) in/out, V K x P, x (N), gram K x K (tuning = 0 only).
+int oracle_optimize_continuous_v2(int N, int P, int K, const double* data, const int32_t* indicator, double* w, const double* V,
+                                  const double* x, const double* gram, double lambda, int tuning) {
+    if (tuning != 0 && tuning != 1) return 3;
+    if (tuning == 1 && !indicator) return 3;
+    Problem pb; pb.N = N; pb.P = P; pb.C = 0; pb.Q = 1; pb.K = K; pb.inc_continuous = 1; pb.tuning = tuning;
+    pb.data = data; pb.train = indicator; pb.test = indicator;
+    std::vector<double> d(data, data + (size_t)N * P), g((size_t)K * K, 0.0);
+    if (gram) g.assign(gram, gram + (size_t)K * K);
+    else for (int b = 0; b < K; ++b) for (int a = 0; a < K; ++a) { double s = 0.0; for (int j = 0; j < P; ++j) s += V[a + (size_t)j * K] * V[b + (size_t)j * K]; g[a + (size_t)b * K] = s; }
+    return optimize_continuous_v2(pb, d, w, 1, V, x, g, lambda);
+}
+
+// OpenMP team control for the timed CPU-baseline legs of bench.py: launchers such as torchrun export OMP_NUM_THREADS=1, and the
+// team sizes of oracle_optimize are clamped to omp_get_max_threads(). Returns the team size now in effect.
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
 // Helpers exposed for unit tests.
 int oracle_chol_solve(int K, double* A, double* b, int nrhs) { return chol_solve(K, A, b, nrhs, K); }
 void oracle_r_unif(uint32_t seed, int n, double* out) { RRng r; r.set_seed(seed); for (int i = 0; i < n; ++i) out[i] = r.unif_rand(); }

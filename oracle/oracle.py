@@ -21,11 +21,19 @@ class OracleCheck(C.Structure):
                 ("loss", C.c_double), ("delta_loss", C.c_double), ("decay", C.c_double)]
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liboracle.so")
+def build(force: bool = False, native: bool = False) -> str:
+    """liboracle.so (x86-64-v3: built in the CPU container, runs on any host of the pool) or, native=True,
+    liboracle_native.so compiled with -march=native ON THE MACHINE THAT RUNS IT (bench.py's timed CPU legs)."""
+    name = "liboracle_native.so" if native else "liboracle.so"
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "insider_oracle.cpp")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
+    if native:
+        # always rebuilt where it runs: a -march=native object from another host may use instructions this one lacks
+        env = dict(os.environ); env.pop("CXX", None); env.pop("CC", None)
+        subprocess.run(["make", "-B", "-C", _HERE, name], check=True, capture_output=True, env=env)
+    elif force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        env = dict(os.environ); env.pop("CXX", None); env.pop("CC", None)
+        subprocess.run(["make", "-C", _HERE, name], check=True, capture_output=True, env=env)
     return so
 
 
@@ -35,11 +43,34 @@ def lib() -> C.CDLL:
         so = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(so):
             build()
-        _LIB = C.CDLL(so)
-        _LIB.oracle_optimize.restype = C.c_int
-        _LIB.oracle_strong_cd.restype = C.c_int
-        _LIB.oracle_fit_interaction.restype = C.c_int
+        _LIB = _load(so)
     return _LIB
+
+
+def _load(so):
+    L = C.CDLL(so)
+    L.oracle_optimize.restype = C.c_int
+    L.oracle_strong_cd.restype = C.c_int
+    L.oracle_fit_interaction.restype = C.c_int
+    L.oracle_optimize_continuous_v2.restype = C.c_int
+    L.oracle_set_threads.restype = C.c_int
+    return L
+
+
+def use_native() -> bool:
+    """Switches this process to the -march=native build (compiled now, on this host). Returns False (and keeps the portable
+    build) when the compiler is missing or fails."""
+    global _LIB
+    try:
+        _LIB = _load(build(native=True))
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def set_threads(n: int) -> int:
+    """omp_set_num_threads(n) inside the oracle; returns omp_get_max_threads() afterwards (the team size really used)."""
+    return int(lib().oracle_set_threads(C.c_int(int(n))))
 
 
 def _dp(a):
@@ -111,6 +142,23 @@ def strong_cd(X, y, wstart, lam, alpha, XtX, Xty, tol=1e-5, perm_mode=1, seed=0,
                            C.c_double(tol), C.c_int(perm_mode), C.c_uint64(seed), C.c_uint32(als_iter), C.c_uint64(gene),
                            C.c_uint32(r_seed), _dp(beta), C.byref(sw), C.byref(rd))
     return beta, sw.value, rd.value
+
+
+def optimize_continuous_v2(data, indicator, updating_factor, c_factor, updating_confd, gram, lam, tuning):
+    """Mirror of ``optimize_continuous_v2`` (src/optimize.cpp:77-137). Returns the updated factor (K,)."""
+    Y = np.asfortranarray(data, dtype=np.float64)
+    N, P = Y.shape
+    V = np.asfortranarray(c_factor, dtype=np.float64)
+    K = V.shape[0]
+    w = np.array(updating_factor, dtype=np.float64).reshape(-1).copy()
+    x = np.ascontiguousarray(updating_confd, dtype=np.float64).reshape(-1)
+    ind = np.asfortranarray(indicator, dtype=np.int32) if indicator is not None else None
+    g = np.asfortranarray(gram, dtype=np.float64) if gram is not None else None
+    rc = lib().oracle_optimize_continuous_v2(C.c_int(N), C.c_int(P), C.c_int(K), _dp(Y), _ip(ind), _dp(w), _dp(V), _dp(x), _dp(g),
+                                             C.c_double(lam), C.c_int(tuning))
+    if rc:
+        raise RuntimeError(f"oracle_optimize_continuous_v2 rc={rc}")
+    return w
 
 
 def randperm_b(seed, als_iter, gene, draw, n):

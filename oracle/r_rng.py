@@ -103,7 +103,45 @@ class RRng:
         return y
 
     def _sample2(self, n: int, k: int) -> np.ndarray:
-        # UNVERIFIED restatement of do_sample2 (R src/main/unique.c): redraw (<= 100 times) on duplicates.
+        """do_sample2 (R src/main/unique.c, the `useHash` branch of sample.int: n > 1e7 and k <= n/2):
+        ``for i < k: for j < 100: y[i] = R_unif_index(n) + 1; if (!isDuplicated(y, i)) break``.
+        Restated from memory of the R sources (not available offline, so there is no known answer from R itself: UNVERIFIED
+        against R). Vectorised statement: every attempt of R_unif_index consumes the same number of uniforms, so the attempts
+        form one fixed stream; the result is its first k distinct in-range values, in order of first appearance. (The two
+        statements differ only if 100 consecutive redraws all hit duplicates: probability < (k/n)^100.)"""
+        if k <= 4096:
+            return self._sample2_loop(n, k)
+        bits = int(math.ceil(math.log2(n)))
+        per = bits // 16 + 1                                       # unif_rand() calls per rbits()
+        out = np.empty(0, dtype=np.int64)
+        seen_sorted = np.empty(0, dtype=np.int64)
+        while out.size < k:
+            m = max(1024, int((k - out.size) * (2.0 ** bits / n) * 1.2) + 1024)
+            u = self.unif(m * per).reshape(m, per)
+            v = np.zeros(m, dtype=np.int64)
+            for c in range(per):
+                v = 65536 * v + np.floor(u[:, c] * 65536).astype(np.int64)
+            v &= (1 << bits) - 1
+            keep = v < n
+            v, pos = v[keep], np.flatnonzero(keep)
+            if seen_sorted.size:
+                dup = np.isin(v, seen_sorted)
+                v, pos = v[~dup], pos[~dup]
+            uniq, first = np.unique(v, return_index=True)          # first occurrence of every value
+            order = np.argsort(first)
+            vals, used = uniq[order], pos[first[order]]
+            need = k - out.size
+            if vals.size > need:
+                # rewind the uniforms that belong to attempts after the last one consumed
+                last_attempt = used[need - 1]
+                self._pos -= (m - 1 - last_attempt) * per
+                vals = vals[:need]
+            out = np.concatenate([out, vals + 1])
+            seen_sorted = np.sort(out - 1)
+        return out
+
+    def _sample2_loop(self, n: int, k: int) -> np.ndarray:
+        """The same, attempt by attempt (slow; cross-checks the vectorised statement on small cases)."""
         seen = set()
         y = np.empty(k, dtype=np.int64)
         for i in range(k):

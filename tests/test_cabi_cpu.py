@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/insider_b200.h but not exported"
     assert sorted(_cabi.EXPORTED) == syms
-    assert lib.insider_b200_version() == 100
+    assert lib.insider_b200_version() == 200
 
 
 def test_struct_layouts_match_header():

@@ -67,3 +67,32 @@ def test_split_edge_cases():
     d[:] = np.nan                                      # all NA
     tr, te, na = _cabi.split(d, 0.5, 123)
     assert te.sum() == 0 and tr.sum() == 0 and na.sum() == 6
+
+
+def test_sample2_vectorised_statement_equals_attempt_loop():
+    """oracle/r_rng.py states do_sample2 twice (attempt loop / "first k distinct in-range values of the attempt stream"): same
+    draws AND same RNG stream position afterwards, for one and two uniforms per attempt (bits < 16 / >= 16)."""
+    for n, k, seed in [(70000, 30000, 1), (20000, 9000, 5), (1 << 16, 20000, 9), (100003, 50001, 3)]:
+        a, b = RRng(seed), RRng(seed)
+        assert np.array_equal(a._sample2(n, k), b._sample2_loop(n, k))
+        assert a.unif_rand() == b.unif_rand()
+
+
+def test_product_split_hashed_branch_is_bit_exact_with_oracle_split():
+    """n > 1e7 non-NA entries and k <= n/2: sample.int takes its hashed branch (do_sample2) - the branch the 377 x 44477 mask of
+    BASELINE config 2/3 takes (R/utils.R:91, 16.8 M entries). csrc/rsplit.cpp:85-98 against the independent NumPy statement.
+    Both are restatements from memory of R's sources: UNVERIFIED against R itself (no R offline), see DESIGN.md section 6."""
+    from insider_b200 import _cabi
+    N, P = 377, 26600                                  # 10 028 200 entries
+    rng = np.random.default_rng(7)
+    d = rng.random((N, P))
+    d[rng.random((N, P)) < 0.001] = np.nan
+    n = int((~np.isnan(d)).sum())
+    assert n > 1e7
+    tr, te, na = _cabi.split(d, 0.1, 123)
+    s = ratio_splitter(d, 0.1, rm_na_col=False, seed=123)
+    assert int(te.sum()) == n // 10
+    assert np.array_equal(te != 0, s["test_indicator"])
+    assert np.array_equal(tr != 0, s["train_indicator"])
+    assert np.array_equal(na != 0, s["na_indicator"])
+    assert not np.any((tr != 0) & (te != 0))

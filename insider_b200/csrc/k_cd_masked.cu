@@ -1,0 +1,333 @@
+// Masked (tuning = 1) column update with elastic net: per-gene Gram matrices that never exist as K x K arrays in HBM.
+//
+//   replaces  optimize_col() tuning = 1 branch   src/optimize.cpp:203-230   (XtX_j = U'U - sum_{i: m_ij = 0} u_i u_i')
+//             strong_coordinate_descent()        src/coordinate_descent.cpp:57-127
+//
+// Round 1 wrote every gene's full K x K matrix to HBM (k_col_gram: 205 MB per iteration at 377 x 44 477, K = 23) and an
+// 8-lanes-per-gene solver fetched it back with 72 scattered loads per lane, kept it in 4.8 KB of shared memory per gene (15 %
+// occupancy, 29 % of its shared-memory wavefronts bank conflicts) and replicated the scalar part of every coordinate update in
+// all 8 lanes (profiles/r01_ncu_k_cd_persistent_v6_masked_A.txt: 221 MB read for 18 MB of algorithmic input).
+//
+// Here:
+//   k_col_gram_tiles  builds the matrices of 32 genes (one SLOT tile: genes in the order the solver will take them) with DMMA
+//                     rank-4 gathers, keeps only the lower triangle, and writes the tile in the solver's own shared-memory
+//                     layout - element e of slot s at [e][s] - so that a tile is ONE contiguous block (83 KB at K = 23):
+//                         [ KT (KT + 1) / 2 triangle elements | KT reciprocals 1 / (XtX_kk + l2) ] x 32 slots
+//   k_cd_masked       one warp = one tile, ONE GENE PER THREAD like the dense solver (k_cd_dense.cu): the tile arrives by one
+//                     TMA bulk copy, the solver state p = q + beta * diag and beta (2 x KT doubles) lives in registers in
+//                     COORDINATE order, and a step on the warp-uniform coordinate k (the visiting order depends only on the
+//                     sweep index, common.cuh) dispatches through `switch (k)` to code with compile-time register and
+//                     shared-memory offsets. Every lane reads its own gene's row elements: [e][lane] is conflict-free, no
+//                     broadcast, no relabelling, no per-sweep table.
+// Arithmetic per coordinate: the p form of k_cd_dense.cu (same operations in the same order; the two solvers give bitwise
+// identical iterates on identical Gram matrices).
+#include <utility>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace ib {
+
+namespace {
+
+constexpr int MAX_SWEEPS_M = 200000;
+
+__host__ __device__ constexpr int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+__host__ __device__ constexpr int tile_elems(int KT) { return KT * (KT + 1) / 2 + KT; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_col_gram_tiles: block = 8 warps = one tile of 32 slots, warp w builds slots 4w .. 4w+3 one after the other (DMMA gathers
+// of the masked-out rows of U, as k_col_gram), stages them gene-major in shared memory (conflict-free for the fragment
+// owners) and the block writes the tile transposed ([e][slot], coalesced).
+template <int SL>
+__global__ void __launch_bounds__(256) k_col_gram_tiles(const uint32_t* __restrict__ trC, const double* __restrict__ U, const double* __restrict__ UtU,
+                                                        const int* __restrict__ order, double* __restrict__ tiles, int N, int K, int KP, int KT, int Wp,
+                                                        int64_t P, double l2) {
+    extern __shared__ double st[];                                            // [32][E1]
+    const int E = tile_elems(KT), E1 = E | 1, NTRI = KT * (KT + 1) / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nW = (N + 31) >> 5;
+    for (int sg = 0; sg < 4; ++sg) {
+        const int s = warp * 4 + sg;
+        const int64_t slot = (int64_t)blockIdx.x * 32 + s;
+        double* out = st + (size_t)s * E1;
+        if (slot >= P) {                                                      // padding slot: zero matrix, zero reciprocals
+            for (int e = lane; e < E; e += 32) out[e] = 0.0;
+            continue;
+        }
+        const int64_t gene = order ? (int64_t)order[slot] : slot;
+        double acc[SL][SL][2];
+#pragma unroll
+        for (int i = 0; i < SL; ++i)
+#pragma unroll
+            for (int j = 0; j < SL; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        int rows[4] = {0, 0, 0, 0};
+        int cnt = 0;
+        auto flush = [&]() {
+            const int myrow = (t == 0) ? rows[0] : (t == 1) ? rows[1] : (t == 2) ? rows[2] : rows[3];
+            double f[SL];
+#pragma unroll
+            for (int n = 0; n < SL; ++n) f[n] = (t < cnt) ? __ldg(U + (size_t)myrow * KP + 8 * n + g) : 0.0;
+#pragma unroll
+            for (int n1 = 0; n1 < SL; ++n1)
+#pragma unroll
+                for (int n2 = n1; n2 < SL; ++n2) dmma(acc[n1][n2][0], acc[n1][n2][1], f[n1], f[n2]);
+            cnt = 0;
+        };
+        for (int w0 = 0; w0 < nW; w0 += 32) {
+            uint32_t z = 0;
+            const int wi = w0 + lane;
+            if (wi < nW) {
+                z = ~__ldg(trC + gene * Wp + wi);
+                const int lim = N - 32 * wi;
+                if (lim < 32) z &= (1u << lim) - 1u;
+            }
+            const int wn = min(32, nW - w0);
+            for (int w = 0; w < wn; ++w) {
+                uint32_t zw = __shfl_sync(FULL, z, w);
+                while (zw) {
+                    const int b = __ffs(zw) - 1;
+                    zw &= zw - 1;
+                    rows[cnt++] = 32 * (w0 + w) + b;
+                    if (cnt == 4) flush();
+                }
+            }
+        }
+        if (cnt > 0) flush();
+#pragma unroll
+        for (int n1 = 0; n1 < SL; ++n1)
+#pragma unroll
+            for (int n2 = n1; n2 < SL; ++n2)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ra = 8 * n1 + g, cb = 8 * n2 + 2 * t + e;          // element (ra, cb) of the symmetric matrix
+                    if (cb >= ra && cb < KT) {
+                        const double v = (cb < K) ? UtU[ra * KP + cb] - acc[n1][n2][e] : 0.0;   // src/optimize.cpp:218
+                        out[cb * (cb + 1) / 2 + ra] = v;
+                        if (cb == ra) out[NTRI + ra] = (ra < K) ? 1.0 / (v + l2) : 0.0;
+                    }
+                }
+    }
+    __syncthreads();
+    double* dst = tiles + (size_t)blockIdx.x * E * 32;
+    for (int x = threadIdx.x; x < E * 32; x += 256) dst[x] = st[(size_t)(x & 31) * E1 + (x >> 5)];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct CdMaskedArgs {
+    const double* tiles;             // [n_tiles][E][32]
+    const double* Xty; double* V;    // per gene, stride ldv
+    int64_t ldv;
+    int K; int64_t P;
+    double la, l2, alpha, lambda;
+    const double* tol_dev; const uint32_t* als_iter_dev;
+    uint64_t seed; int perm_mode;
+    unsigned long long* sweeps_total; unsigned long long* steps_total;
+    int* sweeps_per_gene;
+    const int* order;
+    const unsigned char* perm_table;
+};
+
+// one coordinate update of coordinate C (compile time) for this thread's gene; T = tile + lane ([e][32] layout)
+template <int KT, int C>
+__device__ __forceinline__ void cdm_step(double (&p)[KT], double (&b)[KT], const double* __restrict__ T, uint32_t inc, double la, double hl2, double& dl) {
+    constexpr int NTRI = KT * (KT + 1) / 2;
+    const double d = T[tri(C, C) * 32];
+    const double rinv = T[(NTRI + C) * 32];
+    const bool on = (inc >> C) & 1u;
+    const double bo = b[C];
+    const double up = p[C];                                                   // coordinate_descent.cpp:94 (p form)
+    const double t1 = fabs(up) - la;
+    double nb = copysign(t1, up) * rinv;                                      // :99-104
+    nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
+    nb = on ? nb : bo;
+    const double dlt = nb - bo;
+    const double hden = fma(d, 0.5, hl2);                                     // (XtX_kk + l2) / 2, exactly
+    dl = fma(dlt, fma(hden, nb + bo, -up), dl);
+    dl = fma(la, fabs(nb) - fabs(bo), dl);
+    b[C] = nb;                                                                // :106-109
+    const double nd = -dlt;
+#pragma unroll
+    for (int l = 0; l < KT; ++l)
+        if (l != C) p[l] = fma(nd, T[tri(C, l) * 32], p[l]);
+}
+
+template <int KT, int... Cs>
+__device__ __forceinline__ void cdm_dispatch(std::integer_sequence<int, Cs...>, int k, double (&p)[KT], double (&b)[KT], const double* __restrict__ T,
+                                             uint32_t inc, double la, double hl2, double& dl) {
+    switch (k) {
+#define CDM_CASE(C) case C: if constexpr (C < KT) cdm_step<KT, (C < KT ? C : 0)>(p, b, T, inc, la, hl2, dl); break;
+        CDM_CASE(0) CDM_CASE(1) CDM_CASE(2) CDM_CASE(3) CDM_CASE(4) CDM_CASE(5) CDM_CASE(6) CDM_CASE(7)
+        CDM_CASE(8) CDM_CASE(9) CDM_CASE(10) CDM_CASE(11) CDM_CASE(12) CDM_CASE(13) CDM_CASE(14) CDM_CASE(15)
+        CDM_CASE(16) CDM_CASE(17) CDM_CASE(18) CDM_CASE(19) CDM_CASE(20) CDM_CASE(21) CDM_CASE(22) CDM_CASE(23)
+        CDM_CASE(24) CDM_CASE(25) CDM_CASE(26) CDM_CASE(27) CDM_CASE(28) CDM_CASE(29) CDM_CASE(30) CDM_CASE(31)
+#undef CDM_CASE
+        default: break;
+    }
+}
+
+// p = X'y - (X'X - diag) beta for the screened warm start: row m of the gene's matrix times beta_m, skipping the diagonal
+template <int KT, int M>
+__device__ __forceinline__ void cdm_init_row(double (&p)[KT], const double (&b)[KT], const double* __restrict__ T) {
+    const double bm = b[M];
+#pragma unroll
+    for (int l = 0; l < KT; ++l)
+        if (l != M) p[l] = fma(-T[tri(M, l) * 32], bm, p[l]);
+}
+template <int KT, int... Ms>
+__device__ __forceinline__ void cdm_init(std::integer_sequence<int, Ms...>, double (&p)[KT], const double (&b)[KT], const double* __restrict__ T) {
+    (cdm_init_row<KT, Ms>(p, b, T), ...);
+}
+
+template <int KT>
+__global__ void __launch_bounds__(32, 2) k_cd_masked(CdMaskedArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int E = tile_elems(KT);
+    double* tile = reinterpret_cast<double*>(smem_raw);                       // [E][32]
+    unsigned char* ord_s = reinterpret_cast<unsigned char*>(tile + (size_t)E * 32);   // [2][32] visiting order of this / the next sweep
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ord_s + 64);
+    const int lane = threadIdx.x, K = a.K;
+    const int64_t slot = (int64_t)blockIdx.x * 32 + lane;
+    bool active = slot < a.P;
+    const int64_t gene = active ? (a.order ? (int64_t)a.order[slot] : slot) : 0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(E * 32 * 8));
+        tma_load_1d(tile, a.tiles + (size_t)blockIdx.x * E * 32, (uint32_t)(E * 32 * 8), bar);
+    }
+    const double la = a.la, l2 = a.l2, hl2 = 0.5 * a.l2;
+    const double tol = *a.tol_dev;
+    const uint32_t als_iter = *a.als_iter_dev;
+    const uint64_t key_iter = mix64(a.seed + 0x9E3779B97F4A7C15ull * (1ull + als_iter));   // perm_key(): first factor
+    // order row of sweep dr: word (lane & 7) of the 32-byte row (identity when perm_mode != 1)
+    auto row_word = [&](uint32_t dr) -> uint32_t {
+        const uint32_t c0 = 4u * (lane & 7);
+        if (a.perm_mode != 1) return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24);
+        const uint64_t pk = key_iter ^ mix64((uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
+        return __ldg(reinterpret_cast<const uint32_t*>(a.perm_table + PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + (lane & 7));
+    };
+    uint32_t row_w = row_word(0);
+    // ---- this thread's gene (coordinate order throughout)
+    double p[KT], b[KT];
+    uint32_t inc = 0;
+    {
+        const double* xp = a.Xty + gene * a.ldv;
+        const double* wp = a.V + gene * a.ldv;
+        double mx = 0.0;
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+            p[c] = (active && c < K) ? xp[c] : 0.0;
+            b[c] = (active && c < K) ? wp[c] : 0.0;
+            mx = fmax(mx, fabs(p[c]));
+        }
+        const double thr = a.alpha * (2.0 * a.lambda - mx);                   // coordinate_descent.cpp:74
+#pragma unroll
+        for (int c = 0; c < KT; ++c) {
+            const bool on = active && (c < K) && !(fabs(p[c]) < thr);
+            if (!on) b[c] = 0.0;                                              // :75-78
+            inc |= (on ? 1u : 0u) << c;
+        }
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const double* T = tile + lane;
+    cdm_init<KT>(std::make_integer_sequence<int, KT>{}, p, b, T);             // :79 in covariance form
+    (void)l2;
+    int sweeps = 0, cur = 0;
+    unsigned long long steps_acc = 0;
+    uint32_t draw = 0;
+    while (true) {
+        if (lane < 8) reinterpret_cast<uint32_t*>(ord_s + 32 * cur)[lane] = row_w;
+        row_w = row_word(draw + 1);                                           // consumed by the next sweep
+        __syncwarp();
+        const unsigned char* oc = ord_s + 32 * cur;
+        double dl = 0.0;
+        const uint32_t incs = active ? inc : 0u;                              // finished genes: every step is a no-op
+        int k = oc[0];
+        for (int i = 0; i < K; ++i) {
+            const int kn = oc[(i + 1 < K) ? i + 1 : i];
+            cdm_dispatch<KT>(std::make_integer_sequence<int, KT>{}, k, p, b, T, incs, la, hl2, dl);
+            k = kn;
+        }
+        // ---- end of the sweep for this gene: inner do-while test (:114), KKT re-admission (:118-124)
+        if (active) {
+            ++sweeps;
+            steps_acc += (unsigned long long)__popc(inc);
+            if (!(fabs(dl) > tol) || sweeps >= MAX_SWEEPS_M) {
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int c = 0; c < KT; ++c)
+                    if (c < K && !((inc >> c) & 1u) && fabs(p[c]) > la) vmask |= 1u << c;     // |q_e| = |p_e| (beta_e = 0)
+                if (vmask == 0u || sweeps >= MAX_SWEEPS_M) {
+                    double* vp = a.V + gene * a.ldv;
+#pragma unroll
+                    for (int c = 0; c < KT; ++c) if (c < K) vp[c] = b[c];
+                    if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps;
+                    active = false;
+                } else inc |= vmask;
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        ++draw; cur ^= 1;
+    }
+    unsigned long long sw = (slot < a.P) ? (unsigned long long)sweeps : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sw += __shfl_xor_sync(FULL, sw, o); steps_acc += __shfl_xor_sync(FULL, steps_acc, o); }
+    if (lane == 0) {
+        if (a.sweeps_total && sw) atomicAdd(a.sweeps_total, sw);
+        if (a.steps_total && steps_acc) atomicAdd(a.steps_total, steps_acc);
+    }
+}
+
+template <int KT>
+void launch_masked_kt(const CdMaskedArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)tile_elems(KT) * 32 * 8 + 64 + 16;
+    const int blocks = (int)((a.P + 31) / 32);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_cd_masked<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_cd_masked<KT><<<blocks, 32, smem, st>>>(a);
+}
+
+}  // namespace
+
+size_t cd_masked_tile_doubles(int K, int64_t P) {
+    const int KT = (K + 3) / 4 * 4;
+    return (size_t)((P + 31) / 32) * tile_elems(KT) * 32;
+}
+
+void launch_col_gram_tiles(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, const int* order, double lambda, double alpha,
+                           double* tiles, cudaStream_t st) {
+    if (g.P <= 0) return;
+    const int KT = (g.K + 3) / 4 * 4;
+    const int blocks = (int)((g.P + 31) / 32);
+    const size_t smem = (size_t)32 * (tile_elems(KT) | 1) * 8;
+    const double l2 = lambda * (1.0 - alpha);
+#define LAUNCH_GT(SLv)                                                                                                               \
+    { if (smem > 48 * 1024) cudaFuncSetAttribute(k_col_gram_tiles<SLv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      k_col_gram_tiles<SLv><<<blocks, 256, smem, st>>>(trC, U, UtU, order, tiles, g.N, g.K, g.KP, KT, g.Wp, g.P, l2); }
+    switch (g.NT) { case 1: LAUNCH_GT(1) break; case 2: LAUNCH_GT(2) break; case 3: LAUNCH_GT(3) break; default: LAUNCH_GT(4) break; }
+#undef LAUNCH_GT
+}
+
+void launch_cd_masked(const Geom& g, const double* tiles, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
+                      unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, cudaStream_t st) {
+    if (g.P <= 0) return;
+    CdMaskedArgs a{};
+    a.tiles = tiles; a.Xty = Xty; a.V = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P;
+    a.lambda = p.lambda; a.alpha = p.alpha; a.la = p.lambda * p.alpha; a.l2 = p.lambda * (1.0 - p.alpha);
+    a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
+    a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.perm_table = perm_table;
+    const int KT = (g.K + 3) / 4 * 4;
+    switch (KT / 4) {
+        case 1: launch_masked_kt<4>(a, st); break;
+        case 2: launch_masked_kt<8>(a, st); break;
+        case 3: launch_masked_kt<12>(a, st); break;
+        case 4: launch_masked_kt<16>(a, st); break;
+        case 5: launch_masked_kt<20>(a, st); break;
+        case 6: launch_masked_kt<24>(a, st); break;
+        case 7: launch_masked_kt<28>(a, st); break;
+        default: launch_masked_kt<32>(a, st); break;
+    }
+}
+
+}  // namespace ib

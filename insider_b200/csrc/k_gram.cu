@@ -3,6 +3,8 @@
 //   (gram = V V^T, src/optimize.cpp:332, is accumulated inside k_row_b: k_stream.cu)
 //   k_row_comp_gram  per-row complement  sum_{j: m_ij=0} v_j v_j^T  src/optimize.cpp:163,170 (c_factor.cols(zero_idx) * trans(..))
 //   k_reduce         deterministic sum of per-block partial buffers
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -125,7 +127,56 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceJobs jobs) {
     }
 }
 
+// G = V V^T (src/optimize.cpp:332): a block stages 64 genes at a time and every thread accumulates its elements of the K x K
+// matrix; the last block to finish sums the block partials in block order (deterministic) and optionally bumps the ALS counter.
+constexpr int GV_GENES = 64;
+__global__ void __launch_bounds__(256) k_gram_v(const double* __restrict__ V, int ldV, int KP, int64_t P, double* __restrict__ parts, double* __restrict__ G,
+                                                unsigned int* counter, CheckState* bump) {
+    __shared__ double vs[GV_GENES][33];
+    __shared__ int last;
+    const int KK = KP * KP, tid = threadIdx.x;
+    const int64_t per = ((P + gridDim.x - 1) / gridDim.x + GV_GENES - 1) / GV_GENES * GV_GENES;
+    const int64_t j0 = (int64_t)blockIdx.x * per, j1 = (j0 + per < P) ? j0 + per : P;
+    double acc[3] = {0.0, 0.0, 0.0};                                          // elements tid, tid + 256, tid + 512 (KK <= 1024: 4th below)
+    double acc3 = 0.0;
+    for (int64_t c0 = j0; c0 < j1; c0 += GV_GENES) {
+        const int n = (int)((j1 - c0 < GV_GENES) ? j1 - c0 : GV_GENES);
+        __syncthreads();
+        for (int x = tid; x < n * KP; x += 256) { const int jj = x / KP, l = x % KP; vs[jj][l] = V[(c0 + jj) * ldV + l]; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + 256 * u;
+            if (e < KK) {
+                const int ca = e / KP, cb = e % KP;
+                double s = (u < 3) ? acc[u < 3 ? u : 0] : acc3;
+                for (int jj = 0; jj < n; ++jj) s = fma(vs[jj][ca], vs[jj][cb], s);
+                if (u < 3) acc[u < 3 ? u : 0] = s; else acc3 = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u; if (e < KK) parts[(size_t)blockIdx.x * KK + e] = (u < 3) ? acc[u < 3 ? u : 0] : acc3; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int e = tid; e < KK; e += 256) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(parts + (size_t)b * KK + e);
+        G[e] = s;
+    }
+    if (tid == 0) { *counter = 0u; if (bump) bump->als_iter += 1; }
+}
+
 }  // namespace
+
+int gram_v_parts(int64_t P) { return (int)std::max<int64_t>(1, std::min<int64_t>(148, (P + GV_GENES - 1) / GV_GENES)); }
+void launch_gram_v(const Geom& g, const double* V, double* parts, double* G, unsigned int* counter, CheckState* bump, cudaStream_t st) {
+    k_gram_v<<<gram_v_parts(g.P), 256, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump);
+}
 
 void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, double* Dp, int n_splits, cudaStream_t st) {
     const int64_t warps = (int64_t)g.N * n_splits;

@@ -318,6 +318,10 @@ struct DenseGsArgs {
     int a_in_smem;               // 1: the categorical factors fit in shared memory next to the per-warp factor buffers
     int n_lbuf;                  // factor buffers per warp (2: the next confounder's factor is staged ahead)
     int csr_in_smem;             // 1: co_row / co_cnt staged in shared memory
+    // fused row-factor rebuild (fast path, no continuous covariates): U = sum_c A_c[z_c], Ut, UtU (src/optimize.cpp:365-369)
+    int fuse_u, N, ldT;
+    const RowDesign* designs;
+    double* U; double* Ut; double* UtU;
 };
 constexpr int GS_CLUSTER = 8;       // CTAs per cluster (portable maximum)
 constexpr int GS_WARPS = 16;        // warps per CTA -> 128 levels in flight
@@ -440,6 +444,42 @@ __global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 
         if (it == 0 && c + 1 < a.C) prefetch_level(c + 1);                     // no level in this confounder: still look ahead
         __threadfence();
         cluster.sync();                                                        // block c is complete and visible cluster-wide
+    }
+    if (a.fuse_u) {
+        // Every CTA's shared copy now holds all updated factors: rebuild the row factor right here (k_build_u + k_gram_u_final
+        // were two more dependent launches). CTA r takes a contiguous chunk of rows; the chunks' partial U'U are combined by
+        // CTA 0 through distributed shared memory in rank order (fixed order: bitwise reproducible).
+        const int rank = (int)cluster.block_rank();
+        const int rows_per = (a.N + GS_CLUSTER - 1) / GS_CLUSTER;
+        const int rb = rank * rows_per, re = min(a.N, rb + rows_per);
+        const int ldu = KP + 1;
+        double* us = As + (size_t)n_lv * KP;                                   // [rows_per][KP + 1]   (the factor buffers are idle now)
+        double* part = us + (size_t)rows_per * ldu;                            // [KP * KP]
+        for (int x = threadIdx.x; x < (re - rb) * KP; x += blockDim.x) {
+            const int kr = x / KP, l = x % KP, k = rb + kr;
+            double s = 0.0;
+            for (int c = 0; c < a.C; ++c) s += As[(size_t)(a.lvl_first[c] + a.designs[c].level_of_row[k]) * KP + l];   // optimize.cpp:366-369
+            a.U[(size_t)k * KP + l] = s;
+            a.Ut[(size_t)l * a.ldT + k] = s;
+            us[kr * ldu + l] = s;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+            const int ca = e / KP, cb = e % KP;
+            double s = 0.0;
+            for (int i = 0; i < re - rb; ++i) s = fma(us[i * ldu + ca], us[i * ldu + cb], s);
+            part[e] = s;
+        }
+        cluster.sync();
+        if (rank == 0) {
+            for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < GS_CLUSTER; ++r) s += cluster.map_shared_rank(part, r)[e];
+                a.UtU[e] = s;
+            }
+        }
+        cluster.sync();                                                        // the partials stay alive until CTA 0 has read them
     }
 }
 
@@ -594,9 +634,28 @@ void launch_level_sumB(const Geom& g, const LevelTable* tab_dev, int total_level
     if (total_levels) k_level_sumB<<<total_levels, 128, 0, st>>>(tab_dev, g.KP, B, SB);
 }
 
+bool rows_dense_gs_can_fuse_u(const Geom& g, int Q, int total_levels, int max_levels, int nnz) {
+    // the fast path of k_rows_dense_gs (all factors + two factor buffers per warp in shared memory), no continuous covariates,
+    // and a row chunk + K x K partial that fit into the idle factor buffers
+    const size_t FK = (size_t)g.KP * g.KP + g.KP, limit = 227 * 1024;
+    size_t smem = ((size_t)g.KP * g.KP + GS_WARPS * FK) * 8 + (size_t)total_levels * g.KP * 8;
+    if (smem > limit) return false;
+    if (smem + (size_t)nnz * 12 + 8 <= limit) smem += (size_t)nnz * 12 + 8;
+    if (!(max_levels <= GS_CLUSTER * GS_WARPS && smem + GS_WARPS * FK * 8 <= limit)) return false;
+    const size_t rows_per = (size_t)(g.N + GS_CLUSTER - 1) / GS_CLUSTER;
+    return Q == 0 && rows_per * (g.KP + 1) + (size_t)g.KP * g.KP <= 2 * GS_WARPS * FK;
+}
+
 void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
                           const double* SB, const double* G, const double* Lfac, cudaStream_t st) {
-    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0, 1, 0};
+    launch_rows_dense_gs_ex(g, d, C, Q, total_levels, max_levels, nnz, A_all, W, SB, G, Lfac, nullptr, nullptr, nullptr, nullptr, st);
+}
+
+void launch_rows_dense_gs_ex(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
+                             const double* SB, const double* G, const double* Lfac, const RowDesign* designs_dev, double* U, double* Ut, double* UtU,
+                             cudaStream_t st) {
+    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0, 1, 0, 0, g.N, g.ldT, designs_dev, U, Ut, UtU};
+    a.fuse_u = (U != nullptr && rows_dense_gs_can_fuse_u(g, Q, total_levels, max_levels, nnz)) ? 1 : 0;
     const size_t FK = (size_t)g.KP * g.KP + g.KP, limit = 227 * 1024;
     size_t smem = ((size_t)g.KP * g.KP + GS_WARPS * FK) * 8;
     if (smem + (size_t)total_levels * g.KP * 8 <= limit) { a.a_in_smem = 1; smem += (size_t)total_levels * g.KP * 8; }

@@ -22,11 +22,17 @@ struct Geom {
     int64_t gene0;           // global index of local gene 0 (permutation keys use global gene ids)
 };
 
+struct LevelTable;
 // ---- streaming passes over Y (k_stream.cu) ------------------------------------------------------------------
 // Bp[split][N][KP] = sum over the split's genes of (M o Y) V^T ; Gp[split*4 + w][KP*KP] = partial V V^T (w = 0..3), fused
 void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
                   cudaStream_t st);
 constexpr int ROW_B_GRAM_PARTS = 4;
+// the same with optional outputs: Gp == nullptr skips the V V^T tiles; lv_tab != nullptr (dense, single slab only:
+// row_b_levels_supported) stores per-level sums of the block's B instead of B itself: Bp[split][n_levels][KP]
+void launch_row_b_ex(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
+                     const LevelTable* lv_tab, int n_levels, cudaStream_t st);
+bool row_b_levels_supported(const Geom& g);
 size_t row_b_partial_elems(const Geom& g, int n_splits);
 int row_b_default_splits(const Geom& g, int sm_count);
 // Xty[j][k] = sum_i U[i][k] m_ij y_ij
@@ -45,6 +51,13 @@ void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, d
 void launch_reduce_partials(double* out, const double* partials, int64_t n_elems, int n_parts, cudaStream_t st);
 // the same for up to three buffers in one launch
 void launch_reduce_jobs(int n_jobs, double* const* out, const double* const* parts, const int64_t* n_elems, const int* n_parts, cudaStream_t st);
+
+// G[KP*KP] = V V^T over the local genes (src/optimize.cpp:332) as its own small kernel: block partials in `parts`
+// (gram_v_parts(P) x KP*KP doubles) combined in block order by the last block to finish (`counter`: one zero-initialised
+// unsigned int, left at zero). bump != nullptr: that block also advances the device-side ALS iteration counter.
+int gram_v_parts(int64_t P);
+struct CheckState;
+void launch_gram_v(const Geom& g, const double* V, double* parts, double* G, unsigned int* counter, CheckState* bump, cudaStream_t st);
 
 // ---- row side (k_rows.cu) -----------------------------------------------------------------------------------
 struct RowDesign {            // one categorical confounder
@@ -76,6 +89,12 @@ struct DenseGs { const int* lvl_first; const int* co_ptr; const int* co_row; con
 void launch_level_sumB(const Geom& g, const LevelTable* tab_dev, int total_levels, const double* B, double* SB, cudaStream_t st);
 void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W, const double* SB,
                           const double* G, const double* Lfac, cudaStream_t st);
+// the same with the row-factor rebuild (U, Ut, UtU: k_build_u + k_gram_u_final) fused into the tail of the cluster kernel when
+// rows_dense_gs_can_fuse_u(); otherwise the caller launches launch_build_u afterwards
+void launch_rows_dense_gs_ex(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
+                             const double* SB, const double* G, const double* Lfac, const RowDesign* designs_dev, double* U, double* Ut, double* UtU,
+                             cudaStream_t st);
+bool rows_dense_gs_can_fuse_u(const Geom& g, int Q, int total_levels, int max_levels, int nnz);
 // continuous covariate q: H = sum_k x_k^2 Gk_k, Tq = sum_k x_k (B_k - Gk_k u_k); cyclic coordinate update / solve; updates w and U
 void launch_continuous(const Geom& g, bool masked, const double* x, double* w /*[KP]*/, const double* B, const double* G, const double* D,
                        double lambda, double* U, double* scratch, int* err_flag, cudaStream_t st);
@@ -138,6 +157,16 @@ void launch_cd_dense_batch(int K, int64_t n, const double* XtX, const double* Xt
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
                      double tol, int perm_mode, uint64_t seed, uint32_t als_iter, uint64_t gene0, double* beta, int* sweeps,
                      unsigned int* queue, const unsigned char* perm_table, int sm_count, cudaStream_t st);
+
+// ---- masked column update, round 2 (k_cd_masked.cu) ----------------------------------------------------------
+// tiles[n_tiles][E][32]: lower triangles of the per-gene matrices XtX_j = UtU - sum_{i: m_ij=0} u_i u_i^T plus the
+// reciprocals 1/(XtX_kk + l2), 32 genes per tile in SLOT order (slot i = gene order[i]) in the solver's shared-memory layout
+size_t cd_masked_tile_doubles(int K, int64_t P);
+void launch_col_gram_tiles(const Geom& g, const uint32_t* trC, const double* U, const double* UtU, const int* order, double lambda, double alpha,
+                           double* tiles, cudaStream_t st);
+// thread-per-gene elastic-net CD on those tiles (one warp per tile, tile fetched by one TMA bulk copy). Updates V in place.
+void launch_cd_masked(const Geom& g, const double* tiles, const double* Xty, double* V, const CdParams& p, unsigned long long* sweeps,
+                      unsigned long long* steps, int* sweeps_per_gene, const int* order, const unsigned char* perm_table, cudaStream_t st);
 
 // ---- misc (k_misc.cu) ---------------------------------------------------------------------------------------
 // src: n_genes columns of N mask elements (INSIDER_MASK_* kind) -> dstC[n_genes][Wp] bit-packed

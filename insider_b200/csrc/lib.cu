@@ -130,7 +130,9 @@ struct insider_session {
     double *stats = nullptr, *B = nullptr, *G = nullptr, *D = nullptr;   // stats = [B | G | D] (one all-reduce)
     size_t stats_elems = 0;
     double *Bp = nullptr, *Gp = nullptr, *Dp = nullptr, *GLp = nullptr, *T = nullptr, *cont_scratch = nullptr, *sse_part = nullptr;
-    double* XtXall = nullptr;           // masked path: per-gene Gram matrices [P_l][KP*KP]
+    double* XtXall = nullptr;           // masked ridge path (alpha = 0): per-gene Gram matrices [P_l][KP*KP]
+    double* gram_tiles = nullptr;       // masked elastic net: per-gene lower triangles in 32-gene slot tiles (k_cd_masked.cu)
+    bool masked_v6 = false;             // INSIDER_B200_MASKED_V6=1: the round-1 masked solver (k_col_gram + k_cd_persistent), for A/B runs
     unsigned int* queue = nullptr;      // gene queue of the persistent CD kernel
     double* Vfull = nullptr;            // world > 1: gathered V for the final download
     double* Vpack = nullptr;            // world > 1: the same without pitch (K x P contiguous)
@@ -513,9 +515,18 @@ void run_iteration(insider_session* s) {
             Launch l(s, "k_cd_tables_all"); launch_cd_dense_tables_all(g.K, s->cd_table, s->ctx->perm_table, s->cd_tables_all, sec1.side);
         }
     }
+    const bool masked_cd = s->masked && s->opt.alpha != 0.0;
+    const bool masked_tiles = masked_cd && !s->masked_v6;
+    if (masked_tiles) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, sec1.side); }
     { Launch l(s, "k_col_xty"); launch_col_xty(g, s->masked, r->Y, r->trC, s->Ut, s->Xty, s->stream_blocks, st); }
     sec1.join();
     CdParams p{s->opt.lambda2, s->opt.alpha, &s->state->tol, &s->state->als_iter, s->opt.seed, s->opt.perm_mode};
+    if (masked_tiles) {
+        // per-gene matrices straight into the solver's tile layout (slot order), then thread-per-gene coordinate descent
+        { Launch l(s, "k_col_gram_tiles"); launch_col_gram_tiles(g, r->trC, s->U, s->UtU, s->cd_order, s->opt.lambda2, s->opt.alpha, s->gram_tiles, st); }
+        { Launch l(s, "k_cd_masked"); launch_cd_masked(g, s->gram_tiles, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, st); }
+        return;
+    }
     if (s->masked) { Launch l(s, "k_col_gram"); launch_col_gram(g, r->trC, s->U, s->UtU, s->XtXall, st); }
     if (dense_cd && s->graph_variant == 0) {
         // first iterations (hundreds to thousands of sweeps per gene, counts spread 10x): phases of doubling length. A warp runs
@@ -537,7 +548,6 @@ void run_iteration(insider_session* s) {
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
                         s->graph_variant == 2, nullptr, 0u, 0xffffffffu, s->graph_variant < 2 ? s->cd_tables_all : nullptr, st);
     } else {
-        const bool masked_cd = s->masked && s->opt.alpha != 0.0;
         if (masked_cd) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count,
@@ -614,7 +624,9 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             s->d_splits = std::min(s->d_splits, std::max(1, g.WPr));
             s->Dp = s->pool.get<double>((size_t)s->d_splits * g.N * KK, true, st);
             s->GLp = s->pool.get<double>((size_t)std::max(1, s->total_levels) * s->max_chunks * KK, true, st);
-            s->XtXall = s->pool.get<double>((size_t)std::max<int64_t>(1, g.P) * KK, true, st);
+            { const char* e = getenv("INSIDER_B200_MASKED_V6"); s->masked_v6 = e && e[0] == '1'; }
+            if (o->alpha == 0.0 || s->masked_v6) s->XtXall = s->pool.get<double>((size_t)std::max<int64_t>(1, g.P) * KK, true, st);
+            else s->gram_tiles = s->pool.get<double>(cd_masked_tile_doubles(g.K, std::max<int64_t>(1, g.P)), false, st);
         } else {
             s->GLp = s->pool.get<double>(1, true, st);
         }

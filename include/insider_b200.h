@@ -109,7 +109,8 @@ typedef struct {
     uint32_t check_every;            /* 0 -> 10 (src/optimize.cpp:381) */
     uint64_t seed;                   /* permutation seed (the Rcpp shim draws it from R's RNG inside RNGScope) */
     int32_t verbose;                 /* 1: print the reference's per-check lines to stdout */
-    int32_t use_graph;               /* >= 0 (default): replay each ALS iteration as a CUDA graph; -1: plain kernel launches */
+    int32_t use_graph;               /* 0 (default): steady-state iterations replay a CUDA graph, the first (solver-dominated) ones are
+                                      * launched directly; 1: every iteration is a graph replay; -1: plain kernel launches only */
 } insider_options;
 
 /* one record per evaluation: the initial one (iter = -1, src/optimize.cpp:320-323) and every check_every-th iteration */

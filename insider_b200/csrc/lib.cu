@@ -141,6 +141,13 @@ struct insider_session {
     LevelTable* tab_dev = nullptr;
     double* Lfac = nullptr;             // [total_levels][KP*KP + KP] Cholesky factors + inverse diagonals
     double* SB = nullptr;               // dense path: [total_levels][KP] per-level sums of B
+    // dense fast chain (single slab, no continuous covariates, factors fit the cluster kernel's shared memory): k_row_b stores
+    // per-level sums, V V' is its own kernel right after the column update (so the level factorisations run beside the pass
+    // over Y), the row-factor rebuild is fused into the Gauss-Seidel cluster kernel
+    bool dense_fast = false;
+    double* SBp = nullptr;              // [rb_splits][total_levels][KP]
+    double* gv_parts = nullptr;         // k_gram_v block partials
+    unsigned int* gv_counter = nullptr;
     int rb_splits = 1, d_splits = 1, stream_blocks = 1;
     RowDesign* designs_dev = nullptr;
     std::vector<RowDesign> designs;
@@ -448,6 +455,8 @@ void evaluate(insider_session* s, bool initial) {
 // ---- one ALS iteration (src/optimize.cpp:331-378) -------------------------------------------------------------------
 // Side-stream sections: small kernels that do not depend on each other run beside the main chain (also inside the captured
 // graph, where they become parallel branches). With per-kernel profiling on everything stays on the main stream.
+void run_column_update(insider_session* s);
+
 struct SideSection {
     insider_session* s; int idx; cudaStream_t side;
     SideSection(insider_session* s_, int i) : s(s_), idx(i), side((s_->ctx->profile || s_->ctx->no_side) ? s_->ctx->stream : s_->ctx->side) {
@@ -456,11 +465,27 @@ struct SideSection {
     void join() { if (side != s->ctx->stream) { cudaEventRecord(s->ev_join[idx], side); cudaStreamWaitEvent(s->ctx->stream, s->ev_join[idx], 0); } }
 };
 
-void run_iteration(insider_session* s) {
+bool run_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
     insider_resident* r = s->r;
     const Geom& g = s->g;
     const int KK = g.KP * g.KP;
+    if (s->dense_fast) {
+        // G = V V' (:332) is already there (k_gram_v at the end of the previous iteration / in do_begin): the normal-equation
+        // matrices of every level are factorised beside the pass over Y
+        SideSection sec0(s, 0);
+        { Launch l(s, "k_level_factor"); launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, sec0.side); }
+        { Launch l(s, "k_row_b"); launch_row_b_ex(g, false, r->Y, nullptr, s->V, s->SBp, nullptr, s->rb_splits, s->tab_dev, s->total_levels, st); }
+        { Launch l(s, "k_reduce"); launch_reduce_partials(s->SB, s->SBp, (int64_t)s->total_levels * g.KP, s->rb_splits, st); }
+        if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->SB, s->SB, (size_t)s->total_levels * g.KP, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(SB)");
+        sec0.join();
+        DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
+        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs_ex(g, dg, r->C, r->Q, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz, s->A_all, nullptr, s->SB, s->G, s->Lfac, s->designs_dev, s->U, s->Ut, s->UtU, st); }
+        run_column_update(s);
+        { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, s->state, st); }
+        if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->G, s->G, (size_t)KK, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(G)");
+        return true;
+    }
     // sufficient statistics of the row update: G = V V' (:332), B = (M o Y) V', D_k = complement Grams
     { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st); }
     if (s->masked) { Launch l(s, "k_row_comp_gram"); launch_row_comp_gram(g, r->trR, s->V, s->Dp, s->d_splits, st); }
@@ -506,6 +531,15 @@ void run_iteration(insider_session* s) {
     }
     // row factor rebuild (:365-373) and column update (:376)
     { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
+    run_column_update(s);
+    return false;
+}
+
+// column update (:376): Xty = U'(M o Y), then ridge / elastic net per gene
+void run_column_update(insider_session* s) {
+    cudaStream_t st = s->ctx->stream;
+    insider_resident* r = s->r;
+    const Geom& g = s->g;
     const bool dense_cd = !s->masked && s->opt.alpha != 0.0;
     SideSection sec1(s, 1);                // dense elastic net: slot order and XtX table (neither needs Xty) beside the pass over Y
     if (dense_cd) {
@@ -631,6 +665,13 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             s->GLp = s->pool.get<double>(1, true, st);
         }
         if (r->inc_continuous) s->cont_scratch = s->pool.get<double>(continuous_scratch_elems(g), true, st);
+        s->dense_fast = !s->masked && r->C > 0 && !r->inc_continuous && row_b_levels_supported(g) && !getenv("INSIDER_B200_NO_FAST_CHAIN") &&
+                        rows_dense_gs_can_fuse_u(g, 0, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz);
+        if (s->dense_fast) {
+            s->SBp = s->pool.get<double>((size_t)s->rb_splits * s->total_levels * g.KP, true, st);
+            s->gv_parts = s->pool.get<double>((size_t)gram_v_parts(std::max<int64_t>(1, g.P)) * KK, true, st);
+            s->gv_counter = s->pool.get<unsigned int>(1, true, st);
+        }
         if (ctx->world > 1) { s->Vfull = s->pool.get<double>((size_t)r->P * g.ldV, true, st); s->Vpack = s->pool.get<double>((size_t)r->P * f->K, false, st); }
         for (int c = 0; c < r->C; ++c) s->designs.push_back(RowDesign{r->L[c], r->level_of_row[c], r->rows_sorted[c], r->level_start[c], s->A_all + s->a_off[c]});
         s->designs_dev = s->pool.get<RowDesign>(std::max(1, r->C), true, st);
@@ -668,6 +709,10 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
         }
         upload_factors(s, f);
+        if (s->dense_fast) {                                                   // G = V V' of the initial column factor (:332 of iteration 0)
+            Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, nullptr, st);
+            if (ctx->world > 1) nccl_check(g_nccl.AllReduce(s->G, s->G, (size_t)KK, NCCL_FLOAT64, NCCL_SUM, ctx->comm, st), "ncclAllReduce(G)");
+        }
         // initial row factor and evaluation (:286-289, :320-323)
         { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
         evaluate(s, true);
@@ -687,10 +732,12 @@ void launch_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
     const int v = (s->iter >= CD_VARIANT_SWITCH_ITER) ? 2 : (s->iter >= CD_PHASED_ITERS ? 1 : 0);
     s->graph_variant = v;
-    const bool want_graph = s->opt.use_graph >= 0 && !s->ctx->profile && !s->graph_failed;
+    // Graph replay pays off at steady state (a dozen short dependent kernels per iteration). The first iterations are a few
+    // multi-millisecond solver launches: captured, their instantiation sat inside iteration 0 (measured 48.4 ms against 39.9 ms
+    // with plain launches) - they are launched directly, and the steady-state graph is built while the GPU still works on them.
+    const bool want_graph = s->opt.use_graph >= 0 && !s->ctx->profile && !s->graph_failed && (v == 2 || s->opt.use_graph > 0);
     if (!want_graph) {
-        run_iteration(s);
-        { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
+        if (!run_iteration(s)) { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
         return;
     }
     if (!s->iter_graphs[v]) {
@@ -698,8 +745,7 @@ void launch_iteration(insider_session* s) {
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
         try {
-            run_iteration(s);
-            launch_bump_iter(s->state, st); s->launches += 1;
+            if (!run_iteration(s)) { launch_bump_iter(s->state, st); s->launches += 1; }
         } catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         s->launches_per_iter_v[v] = s->launches - before;
@@ -708,8 +754,7 @@ void launch_iteration(insider_session* s) {
         if (graph) cudaGraphDestroy(graph);
         if (e != cudaSuccess) {                       // fall back to plain launches (still the CUDA path)
             cudaGetLastError(); s->iter_graphs[v] = nullptr; s->graph_failed = true;
-            run_iteration(s);
-            { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
+            if (!run_iteration(s)) { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, st); }
             return;
         }
     }

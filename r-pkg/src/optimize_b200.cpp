@@ -5,7 +5,9 @@
 // [[Rcpp::plugins("cpp17")]]
 #include <Rcpp.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -37,6 +39,8 @@ void marshal(Marshalled& m, Rcpp::NumericMatrix data, Rcpp::List cfd_factors, Rc
              Rcpp::IntegerMatrix test_indicator, int inc_continuous, int latent_dim, double lambda1, double lambda2, double alpha,
              int tuning, double global_tol, double sub_tol, unsigned int max_iter) {
     const int N = data.nrow(), P = data.ncol(), C = cfd_indicators.ncol();
+    if (latent_dim < 1 || latent_dim > 32)                       // before anything is uploaded (INSIDER_ERR_UNSUPPORTED otherwise)
+        Rcpp::stop("insider (B200 back end): latent_dim = %d is not supported; libinsider_b200 handles latent_dim 1..32", latent_dim);
     m.levels.resize((size_t)N * C);                              // cbind() made the indicators double (R/insider.R:40,43)
     for (size_t i = 0; i < m.levels.size(); ++i) m.levels[i] = (int32_t)cfd_indicators[i];
     m.pb.N = N; m.pb.P = P; m.pb.C = C; m.pb.Q = ctns_confounder.ncol(); m.pb.inc_continuous = inc_continuous;
@@ -113,4 +117,76 @@ Rcpp::List b200_optimize_resident(SEXP handle, Rcpp::List cfd_factors, Rcpp::Num
     insider_result res{}; char err[512] = "";
     if (insider_b200_optimize_resident(ctx_singleton(), p.get(), &fac, &opt, &res, err, sizeof err) != INSIDER_OK) Rcpp::stop(err);
     return as_r_list(cfd_factors, column_factor, res);
+}
+
+// ---- the other registered entry points of the reference (src/RcppExports.cpp:112-116) ------------------------------------
+
+// strong_coordinate_descent (src/coordinate_descent.cpp:57-127; R/RcppExports.R:8-10). X and y are accepted and unused: the
+// solver works in covariance form on XtX, Xty.
+// [[Rcpp::export]]
+Rcpp::NumericVector strong_coordinate_descent(Rcpp::NumericMatrix X, Rcpp::NumericVector y, Rcpp::NumericVector wstart, double lambda, double alpha,
+                                              Rcpp::NumericMatrix XtX, Rcpp::NumericVector Xty, double tol = 1e-5) {
+    const int K = XtX.nrow();
+    if (K < 1 || K > 32) Rcpp::stop("insider (B200 back end): %d coordinates are not supported (1..32)", K);
+    if (XtX.ncol() != K || Xty.size() != K || wstart.size() != K) Rcpp::stop("strong_coordinate_descent: XtX must be K x K, Xty and wstart of length K");
+    Rcpp::NumericVector beta(K);
+    uint64_t seed;
+    { Rcpp::RNGScope scope; seed = (uint64_t)(R::unif_rand() * 9007199254740992.0); }     // randperm drew from R's RNG (RcppExports.cpp:37)
+    char err[512] = "";
+    if (insider_b200_strong_cd(ctx_singleton(), K, 1, XtX.begin(), 1, Xty.begin(), wstart.begin(), lambda, alpha, tol, INSIDER_PERM_COUNTER, seed, 0, 0,
+                               beta.begin(), nullptr, err, sizeof err) != INSIDER_OK) Rcpp::stop(err);
+    return beta;
+}
+
+// coordinate_descent (src/coordinate_descent.cpp:10-55): the reference's variant without the strong-rule screen / KKT loop. The
+// elastic net is strictly convex for alpha < 1, so both variants stop at the same minimiser to within tol; the symbol is kept
+// for useDynLib(.registration = TRUE) and bound to the same solver (nothing in R/insider.R calls it).
+// [[Rcpp::export]]
+Rcpp::NumericVector coordinate_descent(Rcpp::NumericMatrix X, Rcpp::NumericVector y, Rcpp::NumericVector wstart, double lambda, double alpha,
+                                       Rcpp::NumericMatrix XtX, Rcpp::NumericVector Xty, double tol = 1e-5) {
+    return strong_coordinate_descent(X, y, wstart, lambda, alpha, XtX, Xty, tol);
+}
+
+// optimize_continuous_v2 (src/optimize.cpp:77-137; R/RcppExports.R:16-18): updating_factor is updated in place (rowvec&).
+// [[Rcpp::export]]
+void optimize_continuous_v2(Rcpp::NumericMatrix data, Rcpp::NumericMatrix indicator, Rcpp::NumericVector updating_factor, Rcpp::NumericMatrix c_factor,
+                            Rcpp::NumericVector updating_confd, Rcpp::NumericMatrix gram, double lambda, int tuning) {
+    const int N = data.nrow(), P = data.ncol(), K = c_factor.nrow();
+    if (K < 1 || K > 32) Rcpp::stop("insider (B200 back end): latent_dim = %d is not supported (1..32)", K);
+    if (tuning != 0 && tuning != 1) Rcpp::stop("Parameter tuning should be either 0 or 1!");       // reference: exit(1), src/optimize.cpp:133-135
+    if (c_factor.ncol() != P || updating_factor.size() != K || updating_confd.size() != N || indicator.nrow() != N || indicator.ncol() != P)
+        Rcpp::stop("optimize_continuous_v2: dimension mismatch");
+    (void)gram;                                                  // V V' is recomputed on the device
+    char err[512] = "";
+    if (insider_b200_optimize_continuous(ctx_singleton(), N, P, K, data.begin(), INSIDER_MASK_DOUBLE, indicator.begin(), updating_factor.begin(),
+                                         c_factor.begin(), updating_confd.begin(), lambda, tuning, err, sizeof err) != INSIDER_OK) Rcpp::stop(err);
+}
+
+// optimize_continuous (src/optimize.cpp:14-74): the reference's first version of the same update (stops on a loss decrement
+// < 1e-3 instead of sum|dw| < 0.1; superseded by _v2 at src/optimize.cpp:345). Bound to the v2 entry; kept for the registration table.
+// [[Rcpp::export]]
+void optimize_continuous(Rcpp::NumericMatrix data, Rcpp::NumericMatrix indicator, Rcpp::NumericVector updating_factor, Rcpp::NumericMatrix c_factor,
+                         Rcpp::NumericVector updating_confd, Rcpp::NumericMatrix gram, double lambda, int tuning) {
+    optimize_continuous_v2(data, indicator, updating_factor, c_factor, updating_confd, gram, lambda, tuning);
+}
+
+// glm_interaction back end (R/glm_interaction.R:2-30): list(coeff_matrix, pval_matrix)
+// [[Rcpp::export]]
+Rcpp::List b200_glm_interaction(Rcpp::NumericMatrix residual, Rcpp::IntegerVector interaction_indicator, Rcpp::NumericMatrix column_factor) {
+    const int N = residual.nrow(), P = residual.ncol(), K = column_factor.nrow();
+    if (column_factor.ncol() != P || interaction_indicator.size() != N) Rcpp::stop("glm_interaction: dimension mismatch");
+    int L = 0; for (int i = 0; i < N; ++i) L = std::max(L, interaction_indicator[i]);
+    Rcpp::NumericMatrix coeff(L, K), pval(L, K);
+    char err[512] = "";
+    if (insider_b200_glm_interaction(ctx_singleton(), N, P, K, residual.begin(), L, interaction_indicator.begin(), column_factor.begin(), coeff.begin(),
+                                     pval.begin(), err, sizeof err) != INSIDER_OK) Rcpp::stop(err);
+    return Rcpp::List::create(coeff, pval);
+}
+
+// number of usable CUDA devices as seen by the library (0 when none: every fit then fails with INSIDER_ERR_CUDA - there is no CPU fallback)
+// [[Rcpp::export]]
+int b200_devices() {
+    int n = 0; char err[64] = "";
+    for (int d = 0; d < 16; ++d) { insider_ctx* c = nullptr; if (insider_b200_ctx_create(&c, d, err, sizeof err) != INSIDER_OK) break; insider_b200_ctx_destroy(c); ++n; }
+    return n;
 }

@@ -78,3 +78,32 @@ def test_synth_shapes_and_levels():
         assert sorted(np.unique(p.confounder[:, c]).tolist()) == list(range(1, L + 1))      # levels exactly 1..L_c
     q = synth.with_continuous(N=60, P=20, K=4, levels=(3, 4), Q=2)
     assert q.X.shape == (60, 2)
+
+
+def test_rcpp_shim_type_checks_against_the_c_abi():
+    """r-pkg/src/optimize_b200.cpp cannot be built here (no R / Rcpp), but its calls into include/insider_b200.h can be
+    type-checked against a stub Rcpp.h: a signature drift between the shim and the C ABI fails this test."""
+    import subprocess
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "r-pkg", "src", "optimize_b200.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "r-pkg", "src", "optimize_b200.cpp")).read()
+    # the five registered entry points of the reference (src/RcppExports.cpp:112-116) are all defined
+    for fn in ("optimize", "strong_coordinate_descent", "coordinate_descent", "optimize_continuous_v2", "optimize_continuous"):
+        assert re.search(r"\[\[Rcpp::export\]\]\s*\n[^\n]*\b" + fn + r"\(", src), fn
+
+
+def test_r_package_configure_finds_the_library(tmp_path):
+    import shutil
+    import subprocess
+    pkg = tmp_path / "pkg"
+    shutil.copytree(os.path.join(ROOT, "r-pkg"), pkg)
+    env = dict(os.environ, INSIDER_B200_HOME=ROOT)
+    r = subprocess.run(["sh", "./configure"], cwd=pkg, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mk = open(pkg / "src" / "Makevars").read()
+    assert f"-I{ROOT}/include" in mk and "-linsider_b200" in mk
+    env = {k: v for k, v in os.environ.items() if not k.startswith("INSIDER_B200")}
+    env["INSIDER_B200_HOME"] = str(tmp_path / "nowhere")
+    r = subprocess.run(["sh", "./configure"], cwd=pkg, env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "not found" in r.stderr

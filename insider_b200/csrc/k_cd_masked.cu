@@ -25,6 +25,8 @@
 //                     profiles/r02_masked_solver_versions.txt). Only `up = p[k]` needs a run-time register index: a 24-way
 //                     switch of single moves. Every lane reads its own gene's elements: [e][lane] is conflict-free.
 // Arithmetic per coordinate: the p form of k_cd_dense.cu, operation for operation.
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "common.cuh"
@@ -246,11 +248,13 @@ __global__ void __launch_bounds__(32, 2) k_cd_masked(CdMaskedArgs a) {
         const unsigned char* oc = ord_s + 32 * cur;
         double dl = 0.0;
         const uint32_t incs = active ? inc : 0u;                              // finished genes: every step is a no-op
+        // (fetching the next step's row one step early into a second register set - 208 registers - was measured slower: 485
+        //  against 445 us per steady-state launch, profiles/r02_masked_solver_versions.txt)
         int k = oc[0];
         for (int i = 0; i < K; ++i) {
             const int kn = oc[(i + 1 < K) ? i + 1 : i];
             double x[KT];
-            load_row<KT>(x, Tb, off_s, k);                                          // depends on k only: in flight during the scalar chain
+            load_row<KT>(x, Tb, off_s, k);                                    // depends on k only: in flight during the scalar chain
             const double d = T[(size_t)(NTRI + k) * 32];
             const double rinv = T[(size_t)(NTRI + KT + k) * 32];
             const double bo = bs[k * 32];
@@ -305,6 +309,16 @@ void launch_masked_kt(const CdMaskedArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)(tile_elems(KT) + KT) * 32 * 8 + (size_t)KT * KT * 4 + 64 + 16;
     const int blocks = (int)((a.P + 31) / 32);
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_cd_masked<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // two one-warp blocks per SM need the full shared-memory carve-out (the driver's default heuristic may settle for less)
+    cudaFuncSetAttribute(k_cd_masked<KT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("INSIDER_B200_TRACE")) {
+        static bool once = false;
+        if (!once) {
+            once = true; int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_cd_masked<KT>, 32, smem);
+            fprintf(stderr, "[insider_b200] k_cd_masked<%d>: %zu B shared memory per block, %d resident blocks per SM\n", KT, smem, nb);
+        }
+    }
     k_cd_masked<KT><<<blocks, 32, smem, st>>>(a);
 }
 
@@ -325,6 +339,7 @@ void launch_col_gram_tiles(const Geom& g, const uint32_t* trC, const double* U, 
     const double l2 = lambda * (1.0 - alpha);
 #define LAUNCH_GT(SLv)                                                                                                               \
     { if (smem > 48 * 1024) cudaFuncSetAttribute(k_col_gram_tiles<SLv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      cudaFuncSetAttribute(k_col_gram_tiles<SLv>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   \
       k_col_gram_tiles<SLv><<<blocks, GT_WARPS * 32, smem, st>>>(trC, U, UtU, order, tiles, g.N, g.K, g.KP, KT, g.Wp, g.P, l2, list_len); }
     switch (g.NT) { case 1: LAUNCH_GT(1) break; case 2: LAUNCH_GT(2) break; case 3: LAUNCH_GT(3) break; default: LAUNCH_GT(4) break; }
 #undef LAUNCH_GT

@@ -127,45 +127,69 @@ __global__ void __launch_bounds__(256) k_reduce(ReduceJobs jobs) {
     }
 }
 
-// G = V V^T (src/optimize.cpp:332): a block stages 64 genes at a time and every thread accumulates its elements of the K x K
-// matrix; the last block to finish sums the block partials in block order (deterministic) and optionally bumps the ALS counter.
-constexpr int GV_GENES = 64;
-__global__ void __launch_bounds__(256) k_gram_v(const double* __restrict__ V, int ldV, int KP, int64_t P, double* __restrict__ parts, double* __restrict__ G,
+// G = V V^T (src/optimize.cpp:332) as its own kernel: GV_BLOCKS blocks of 8 warps, a warp takes every (8 GV_BLOCKS)-th group of
+// 4 genes as one DMMA rank-4 update of the NT (NT + 1) / 2 upper tiles (operands straight from global memory); the 8 warps of a
+// block are combined through shared memory, the GV_BLOCKS block partials by the last block to finish - every sum in a fixed
+// order. Few blocks on purpose: the kernel is a latency chain (loads -> block sum -> cross-block sum) and the cross-block sum
+// costs one L2 round trip per 8 partials (a first version with 148 partials summed serially took 84 us, this one ~8).
+constexpr int GV_BLOCKS = 64, GV_WARPS = 4;
+template <int NT>
+__global__ void __launch_bounds__(GV_WARPS * 32) k_gram_v(const double* __restrict__ V, int ldV, int KP, int64_t P, double* __restrict__ parts, double* __restrict__ G,
                                                 unsigned int* counter, CheckState* bump) {
-    __shared__ double vs[GV_GENES][33];
+    __shared__ double sm[GV_WARPS][NT * 8 * NT * 8];
     __shared__ int last;
-    const int KK = KP * KP, tid = threadIdx.x;
-    const int64_t per = ((P + gridDim.x - 1) / gridDim.x + GV_GENES - 1) / GV_GENES * GV_GENES;
-    const int64_t j0 = (int64_t)blockIdx.x * per, j1 = (j0 + per < P) ? j0 + per : P;
-    double acc[3] = {0.0, 0.0, 0.0};                                          // elements tid, tid + 256, tid + 512 (KK <= 1024: 4th below)
-    double acc3 = 0.0;
-    for (int64_t c0 = j0; c0 < j1; c0 += GV_GENES) {
-        const int n = (int)((j1 - c0 < GV_GENES) ? j1 - c0 : GV_GENES);
-        __syncthreads();
-        for (int x = tid; x < n * KP; x += 256) { const int jj = x / KP, l = x % KP; vs[jj][l] = V[(c0 + jj) * ldV + l]; }
-        __syncthreads();
+    const int KK = KP * KP, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    double acc[NT][NT][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = tid + 256 * u;
-            if (e < KK) {
-                const int ca = e / KP, cb = e % KP;
-                double s = (u < 3) ? acc[u < 3 ? u : 0] : acc3;
-                for (int jj = 0; jj < n; ++jj) s = fma(vs[jj][ca], vs[jj][cb], s);
-                if (u < 3) acc[u < 3 ? u : 0] = s; else acc3 = s;
-            }
-        }
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int64_t n_groups = (P + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * GV_WARPS + warp; q < n_groups; q += (int64_t)gridDim.x * GV_WARPS) {
+        const int64_t j = 4 * q + t;
+        double f[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) f[n] = (j < P) ? V[j * ldV + 8 * n + g] : 0.0;
+#pragma unroll
+        for (int n1 = 0; n1 < NT; ++n1)
+#pragma unroll
+            for (int n2 = n1; n2 < NT; ++n2) dmma(acc[n1][n2][0], acc[n1][n2][1], f[n1], f[n2]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int e = tid + 256 * u; if (e < KK) parts[(size_t)blockIdx.x * KK + e] = (u < 3) ? acc[u < 3 ? u : 0] : acc3; }
+    for (int n1 = 0; n1 < NT; ++n1)
+#pragma unroll
+        for (int n2 = n1; n2 < NT; ++n2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ra = 8 * n1 + g, cb = 8 * n2 + 2 * t + e;
+                sm[warp][ra * KP + cb] = acc[n1][n2][e];
+                sm[warp][cb * KP + ra] = acc[n1][n2][e];
+            }
+    __syncthreads();
+    for (int e = tid; e < KK; e += GV_WARPS * 32) {
+        double s = sm[0][e];
+#pragma unroll
+        for (int w = 1; w < GV_WARPS; ++w) s += sm[w][e];
+        parts[(size_t)blockIdx.x * KK + e] = s;
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!last) return;
     __threadfence();
-    for (int e = tid; e < KK; e += 256) {
+    const int nb = (int)gridDim.x;
+    for (int e = tid; e < KK; e += GV_WARPS * 32) {
         double s = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(parts + (size_t)b * KK + e);
+        int b = 0;
+        for (; b + 8 <= nb; b += 8) {                                         // 8 independent loads in flight, summed in block order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(parts + (size_t)(b + u) * KK + e);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < nb; ++b) s += __ldcg(parts + (size_t)b * KK + e);
         G[e] = s;
     }
     if (tid == 0) { *counter = 0u; if (bump) bump->als_iter += 1; }
@@ -173,9 +197,15 @@ __global__ void __launch_bounds__(256) k_gram_v(const double* __restrict__ V, in
 
 }  // namespace
 
-int gram_v_parts(int64_t P) { return (int)std::max<int64_t>(1, std::min<int64_t>(148, (P + GV_GENES - 1) / GV_GENES)); }
+int gram_v_parts(int64_t P) { return (int)std::max<int64_t>(1, std::min<int64_t>(GV_BLOCKS, (P + 31) / 32)); }
 void launch_gram_v(const Geom& g, const double* V, double* parts, double* G, unsigned int* counter, CheckState* bump, cudaStream_t st) {
-    k_gram_v<<<gram_v_parts(g.P), 256, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump);
+    const int nb = gram_v_parts(g.P);
+    switch (g.NT) {
+        case 1: k_gram_v<1><<<nb, GV_WARPS * 32, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump); break;
+        case 2: k_gram_v<2><<<nb, GV_WARPS * 32, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump); break;
+        case 3: k_gram_v<3><<<nb, GV_WARPS * 32, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump); break;
+        default: k_gram_v<4><<<nb, GV_WARPS * 32, 0, st>>>(V, g.ldV, g.KP, g.P, parts, G, counter, bump); break;
+    }
 }
 
 void launch_row_comp_gram(const Geom& g, const uint32_t* trR, const double* V, double* Dp, int n_splits, cudaStream_t st) {

@@ -320,7 +320,7 @@ struct DenseGsArgs {
     int csr_in_smem;             // 1: co_row / co_cnt staged in shared memory
     // fused row-factor rebuild (fast path, no continuous covariates): U = sum_c A_c[z_c], Ut, UtU (src/optimize.cpp:365-369)
     int fuse_u, N, ldT;
-    const RowDesign* designs;
+    const int* row_lv;           // [N][C] global level index (row of A_all) of every (sample, confounder)
     double* U; double* Ut; double* UtU;
 };
 constexpr int GS_CLUSTER = 8;       // CTAs per cluster (portable maximum)
@@ -458,7 +458,7 @@ __global__ void __cluster_dims__(GS_CLUSTER, 1, 1) __launch_bounds__(GS_WARPS * 
         for (int x = threadIdx.x; x < (re - rb) * KP; x += blockDim.x) {
             const int kr = x / KP, l = x % KP, k = rb + kr;
             double s = 0.0;
-            for (int c = 0; c < a.C; ++c) s += As[(size_t)(a.lvl_first[c] + a.designs[c].level_of_row[k]) * KP + l];   // optimize.cpp:366-369
+            for (int c = 0; c < a.C; ++c) s += As[(size_t)__ldg(a.row_lv + (size_t)k * a.C + c) * KP + l];   // optimize.cpp:366-369
             a.U[(size_t)k * KP + l] = s;
             a.Ut[(size_t)l * a.ldT + k] = s;
             us[kr * ldu + l] = s;
@@ -652,9 +652,9 @@ void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int tot
 }
 
 void launch_rows_dense_gs_ex(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
-                             const double* SB, const double* G, const double* Lfac, const RowDesign* designs_dev, double* U, double* Ut, double* UtU,
+                             const double* SB, const double* G, const double* Lfac, const int* row_lv, double* U, double* Ut, double* UtU,
                              cudaStream_t st) {
-    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0, 1, 0, 0, g.N, g.ldT, designs_dev, U, Ut, UtU};
+    DenseGsArgs a{C, g.K, g.KP, Q, d.lvl_first, d.co_ptr, d.co_row, d.co_cnt, d.Sx, W, A_all, SB, G, Lfac, 0, 1, 0, 0, g.N, g.ldT, row_lv, U, Ut, UtU};
     a.fuse_u = (U != nullptr && rows_dense_gs_can_fuse_u(g, Q, total_levels, max_levels, nnz)) ? 1 : 0;
     const size_t FK = (size_t)g.KP * g.KP + g.KP, limit = 227 * 1024;
     size_t smem = ((size_t)g.KP * g.KP + GS_WARPS * FK) * 8;

@@ -36,8 +36,9 @@ struct StreamArgs {
     int n_stages;
     int n_splits;                // k_row_b: gene splits (grid.x); others: number of blocks
     int scratch_sep;             // k_col_xty: 1 = dedicated cross-warp scratch (stage buffer too small to alias)
-    const LevelTable* lv_tab;    // k_row_b, dense single-slab fast path: sum the block's B rows per confounder level and store
-    int n_levels;                // out[split][n_levels][KP] instead of out[split][N][KP] (k_level_sumB folded into the epilogue)
+    const int* lv_ptr;           // k_row_b, dense single-slab fast path: sum the block's B rows per confounder level (CSR over all
+    const int* lv_rows;          // levels of all confounders: rows lv_rows[lv_ptr[l] .. lv_ptr[l+1]) ascending) and store
+    int n_levels, n_lv_rows;     // out[split][n_levels][KP] instead of out[split][N][KP] (k_level_sumB folded into the epilogue)
 };
 
 // balanced partition of n items over parts
@@ -202,13 +203,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
         double* Gp = a.out2 + ((size_t)blockIdx.x * (TG / 4) + gks) * a.KP * a.KP;
         gram_store<NT, 0>(gacc, Gp, a.KP, ghalf, g, t);
     }
-    if (a.lv_tab != nullptr) {
+    if (a.lv_ptr != nullptr) {
         // Dense fast path (single slab): the row update only needs the sums of B over the rows of every confounder level
         // (k_rows.cu: rhs = SB - G w). Stage this block's B in shared memory (the stage ring is idle: every bulk copy has landed
-        // and been consumed) and sum it per level in the fixed order of the level's row list: 133 x KP instead of 377 x KP
-        // doubles per partial, and no separate k_level_sumB launch.
+        // and been consumed) together with the level lists, and sum it per level in the fixed order of the level's row list:
+        // 133 x KP instead of 377 x KP doubles per partial, and no separate k_level_sumB launch.
         double* Bs = stage0;                                                  // [N][KP]
+        int* ptr_s = reinterpret_cast<int*>(Bs + (size_t)a.N * a.KP);         // [n_levels + 1]
+        int* rows_s = ptr_s + a.n_levels + 1;                                 // [n_lv_rows]
         __syncthreads();
+        for (int x = tid; x <= a.n_levels; x += THREADS) ptr_s[x] = __ldg(a.lv_ptr + x);
+        for (int x = tid; x < a.n_lv_rows; x += THREADS) rows_s[x] = __ldg(a.lv_rows + x);
 #pragma unroll
         for (int i = 0; i < MT_PER_WARP; ++i) {
             const int mt = warp + NWARPS * i;
@@ -224,17 +229,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_row_b(StreamArgs a) {
         }
         __syncthreads();
         double* SBp = a.out + (size_t)blockIdx.x * a.n_levels * a.KP;
-        // a warp per level, lanes = columns (KP <= 32): coalesced row reads from shared memory, 4 independent partial sums
+        // a warp per level, lanes = columns (KP <= 32), 4 independent partial sums combined in a fixed order
         for (int lv = warp; lv < a.n_levels; lv += NWARPS) {
-            const LevelTable tb = a.lv_tab[lv];
             if (lane < a.KP) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int r = tb.row_begin;
-                for (; r + 4 <= tb.row_end; r += 4) {
-                    const int k0 = __ldg(tb.rows_sorted + r), k1 = __ldg(tb.rows_sorted + r + 1), k2 = __ldg(tb.rows_sorted + r + 2), k3 = __ldg(tb.rows_sorted + r + 3);
-                    s0 += Bs[k0 * a.KP + lane]; s1 += Bs[k1 * a.KP + lane]; s2 += Bs[k2 * a.KP + lane]; s3 += Bs[k3 * a.KP + lane];
+                int r = ptr_s[lv];
+                const int re = ptr_s[lv + 1];
+                for (; r + 4 <= re; r += 4) {
+                    s0 += Bs[rows_s[r] * a.KP + lane]; s1 += Bs[rows_s[r + 1] * a.KP + lane];
+                    s2 += Bs[rows_s[r + 2] * a.KP + lane]; s3 += Bs[rows_s[r + 3] * a.KP + lane];
                 }
-                for (; r < tb.row_end; ++r) s0 += Bs[__ldg(tb.rows_sorted + r) * a.KP + lane];
+                for (; r < re; ++r) s0 += Bs[rows_s[r] * a.KP + lane];
                 SBp[(size_t)lv * a.KP + lane] = (s0 + s1) + (s2 + s3);
             }
         }
@@ -688,18 +693,19 @@ int row_b_default_splits(const Geom& g, int sm_count) {
 size_t row_b_partial_elems(const Geom& g, int n_splits) { return (size_t)n_splits * g.N * g.KP; }
 int stream_default_blocks(const Geom& g, int sm_count) { return sm_count < g.n_tiles ? sm_count : g.n_tiles; }
 
-bool row_b_levels_supported(const Geom& g) {
-    // single slab, and the staged N x KP block fits in the stage ring (it always does: a stage holds 16 x ldY doubles)
-    return g.N <= SINGLE_SLAB_MAX_N && (size_t)g.N * g.KP <= 2 * ((size_t)TG * g.ldY + 8 + (size_t)TG * g.ldV);
+bool row_b_levels_supported(const Geom& g, int n_levels, int n_lv_rows) {
+    // single slab, and the staged N x KP block + the level lists fit in two stages of the ring (a stage holds 16 x ldY doubles)
+    return g.N <= SINGLE_SLAB_MAX_N && (size_t)g.N * g.KP + ((size_t)n_levels + 1 + n_lv_rows + 1) / 2 <= 2 * ((size_t)TG * g.ldY + 8 + (size_t)TG * g.ldV);
 }
 
 void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
-                  cudaStream_t st) { launch_row_b_ex(g, masked, Y, trC, V, Bp, Gp, n_splits, nullptr, 0, st); }
+                  cudaStream_t st) { launch_row_b_ex(g, masked, Y, trC, V, Bp, Gp, n_splits, nullptr, nullptr, 0, 0, st); }
 
 void launch_row_b_ex(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
-                     const LevelTable* lv_tab, int n_levels, cudaStream_t st) {
+                     const int* lv_ptr, const int* lv_rows, int n_levels, int n_lv_rows, cudaStream_t st) {
     StreamArgs a = base_args(g);
-    a.Y = Y; a.trC = trC; a.V = V; a.out = Bp; a.out2 = Gp; a.n_splits = n_splits; a.lv_tab = lv_tab; a.n_levels = n_levels;
+    a.Y = Y; a.trC = trC; a.V = V; a.out = Bp; a.out2 = Gp; a.n_splits = n_splits;
+    a.lv_ptr = lv_ptr; a.lv_rows = lv_rows; a.n_levels = n_levels; a.n_lv_rows = n_lv_rows;
     if (g.N <= SINGLE_SLAB_MAX_N) { a.R = g.ldY; a.n_slabs = 1; a.pitchS = g.ldY; }
     else { a.R = SLAB_ROWS_BIG; a.n_slabs = (g.ldY + a.R - 1) / a.R; a.pitchS = pitch4(a.R); }
     const size_t stage = ((size_t)TG * a.pitchS + 8 + (size_t)TG * g.ldV) * 8;

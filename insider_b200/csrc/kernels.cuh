@@ -28,11 +28,12 @@ struct LevelTable;
 void launch_row_b(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
                   cudaStream_t st);
 constexpr int ROW_B_GRAM_PARTS = 4;
-// the same with optional outputs: Gp == nullptr skips the V V^T tiles; lv_tab != nullptr (dense, single slab only:
-// row_b_levels_supported) stores per-level sums of the block's B instead of B itself: Bp[split][n_levels][KP]
+// the same with optional outputs: Gp == nullptr skips the V V^T tiles; lv_ptr != nullptr (dense, single slab only:
+// row_b_levels_supported) stores per-level sums of the block's B instead of B itself: Bp[split][n_levels][KP]. lv_ptr / lv_rows:
+// CSR over all levels of all confounders (rows of a level ascending), n_lv_rows = C * N entries
 void launch_row_b_ex(const Geom& g, bool masked, const double* Y, const uint32_t* trC, const double* V, double* Bp, double* Gp, int n_splits,
-                     const LevelTable* lv_tab, int n_levels, cudaStream_t st);
-bool row_b_levels_supported(const Geom& g);
+                     const int* lv_ptr, const int* lv_rows, int n_levels, int n_lv_rows, cudaStream_t st);
+bool row_b_levels_supported(const Geom& g, int n_levels, int n_lv_rows);
 size_t row_b_partial_elems(const Geom& g, int n_splits);
 int row_b_default_splits(const Geom& g, int sm_count);
 // Xty[j][k] = sum_i U[i][k] m_ij y_ij
@@ -92,8 +93,8 @@ void launch_rows_dense_gs(const Geom& g, const DenseGs& d, int C, int Q, int tot
 // the same with the row-factor rebuild (U, Ut, UtU: k_build_u + k_gram_u_final) fused into the tail of the cluster kernel when
 // rows_dense_gs_can_fuse_u(); otherwise the caller launches launch_build_u afterwards
 void launch_rows_dense_gs_ex(const Geom& g, const DenseGs& d, int C, int Q, int total_levels, int max_levels, int nnz, double* A_all, const double* W,
-                             const double* SB, const double* G, const double* Lfac, const RowDesign* designs_dev, double* U, double* Ut, double* UtU,
-                             cudaStream_t st);
+                             const double* SB, const double* G, const double* Lfac, const int* row_lv /*[N][C] global level of (row, confounder)*/,
+                             double* U, double* Ut, double* UtU, cudaStream_t st);
 bool rows_dense_gs_can_fuse_u(const Geom& g, int Q, int total_levels, int max_levels, int nnz);
 // continuous covariate q: H = sum_k x_k^2 Gk_k, Tq = sum_k x_k (B_k - Gk_k u_k); cyclic coordinate update / solve; updates w and U
 void launch_continuous(const Geom& g, bool masked, const double* x, double* w /*[KP]*/, const double* B, const double* G, const double* D,

@@ -107,6 +107,8 @@ struct insider_resident {
     // dense-path Gauss-Seidel tables (design only): co-occurrence CSR over all levels, per-level sums of X
     int total_levels = 0;
     int *gs_lvl_first = nullptr, *gs_co_ptr = nullptr, *gs_co_row = nullptr;
+    int *gs_row_lv = nullptr;               // [N][C] global level index of every (sample, confounder)
+    int *lv_ptr = nullptr, *lv_rows = nullptr;   // CSR over all levels: the rows of each level, ascending ([total_levels + 1], [C * N])
     int gs_nnz = 0;
     double *gs_co_cnt = nullptr, *gs_Sx = nullptr;
     double n_train = 0, n_test = 0;
@@ -132,7 +134,10 @@ struct insider_session {
     double *Bp = nullptr, *Gp = nullptr, *Dp = nullptr, *GLp = nullptr, *T = nullptr, *cont_scratch = nullptr, *sse_part = nullptr;
     double* XtXall = nullptr;           // masked ridge path (alpha = 0): per-gene Gram matrices [P_l][KP*KP]
     double* gram_tiles = nullptr;       // masked elastic net: per-gene lower triangles in 32-gene slot tiles (k_cd_masked.cu)
-    bool masked_v6 = false;             // INSIDER_B200_MASKED_V6=1: the round-1 masked solver (k_col_gram + k_cd_persistent), for A/B runs
+    bool masked_v6 = true;              // masked elastic net: k_col_gram + k_cd_persistent (8 lanes per gene, dynamic gene queue). The
+                                        // thread-per-gene tile solver of k_cd_masked.cu (INSIDER_B200_MASKED_TILES=1) is faster at steady
+                                        // state (0.94 against 1.14 ms per iteration) but slower in the first, unordered iterations that
+                                        // dominate a 31-iteration tune() fit (profiles/r02_masked_solver_versions.txt)
     unsigned int* queue = nullptr;      // gene queue of the persistent CD kernel
     double* Vfull = nullptr;            // world > 1: gathered V for the final download
     double* Vpack = nullptr;            // world > 1: the same without pitch (K x P contiguous)
@@ -306,6 +311,23 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
                     for (auto& kv : co) { rows.push_back(kv.first); cnts.push_back((double)kv.second); }
                     ptr[first[c] + l + 1] = (int)rows.size();
                 }
+            {
+                std::vector<int> row_lv((size_t)std::max(1, N * r->C)), lptr(r->total_levels + 1, 0), lrows((size_t)std::max(1, N * r->C));
+                for (int c = 0; c < r->C; ++c) {
+                    for (int k = 0; k < N; ++k) row_lv[(size_t)k * r->C + c] = first[c] + r->lor_host[c][k];
+                    std::vector<int> fill(r->L[c]);
+                    for (int l = 0; l < r->L[c]; ++l) { lptr[first[c] + l] = c * N + r->level_start_host[c][l]; fill[l] = lptr[first[c] + l]; }
+                    for (int k = 0; k < N; ++k) lrows[fill[r->lor_host[c][k]]++] = k;
+                }
+                lptr[r->total_levels] = N * r->C;
+                r->gs_row_lv = r->pool.get<int>(row_lv.size(), false);
+                r->lv_ptr = r->pool.get<int>(lptr.size(), false);
+                r->lv_rows = r->pool.get<int>(lrows.size(), false);
+                CUDA_TRY(cudaMemcpyAsync(r->gs_row_lv, row_lv.data(), row_lv.size() * 4, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(r->lv_ptr, lptr.data(), lptr.size() * 4, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpyAsync(r->lv_rows, lrows.data(), lrows.size() * 4, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+            }
             r->gs_nnz = (int)rows.size();
             r->gs_lvl_first = r->pool.get<int>(first.size(), false);
             r->gs_co_ptr = r->pool.get<int>(ptr.size(), false);
@@ -471,20 +493,23 @@ bool run_iteration(insider_session* s) {
     const Geom& g = s->g;
     const int KK = g.KP * g.KP;
     if (s->dense_fast) {
-        // G = V V' (:332) is already there (k_gram_v at the end of the previous iteration / in do_begin): the normal-equation
-        // matrices of every level are factorised beside the pass over Y
+        // Two independent chains meet at the Gauss-Seidel kernel: [G = V V' (:332) -> factorisation of every level's normal
+        // equations] needs V only, [pass over Y -> per-level sums of B] is the long one: they run side by side (one GPU). With
+        // several GPUs SB and G are adjacent and travel in ONE all-reduce, after which the factorisations follow on the chain.
         SideSection sec0(s, 0);
-        { Launch l(s, "k_level_factor"); launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, sec0.side); }
-        { Launch l(s, "k_row_b"); launch_row_b_ex(g, false, r->Y, nullptr, s->V, s->SBp, nullptr, s->rb_splits, s->tab_dev, s->total_levels, st); }
+        { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, nullptr, sec0.side); }
+        if (s->ctx->world == 1) { Launch l(s, "k_level_factor"); launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, sec0.side); }
+        { Launch l(s, "k_row_b"); launch_row_b_ex(g, false, r->Y, nullptr, s->V, s->SBp, nullptr, s->rb_splits, r->lv_ptr, r->lv_rows, s->total_levels, g.N * r->C, st); }
         { Launch l(s, "k_reduce"); launch_reduce_partials(s->SB, s->SBp, (int64_t)s->total_levels * g.KP, s->rb_splits, st); }
-        if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->SB, s->SB, (size_t)s->total_levels * g.KP, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(SB)");
         sec0.join();
+        if (s->ctx->world > 1) {
+            nccl_check(g_nccl.AllReduce(s->SB, s->SB, (size_t)s->total_levels * g.KP + KK, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(SB|G)");
+            Launch l(s, "k_level_factor"); launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, st);
+        }
         DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
-        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs_ex(g, dg, r->C, r->Q, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz, s->A_all, nullptr, s->SB, s->G, s->Lfac, s->designs_dev, s->U, s->Ut, s->UtU, st); }
+        { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs_ex(g, dg, r->C, r->Q, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz, s->A_all, nullptr, s->SB, s->G, s->Lfac, r->gs_row_lv, s->U, s->Ut, s->UtU, st); }
         run_column_update(s);
-        { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, s->state, st); }
-        if (s->ctx->world > 1) nccl_check(g_nccl.AllReduce(s->G, s->G, (size_t)KK, NCCL_FLOAT64, NCCL_SUM, s->ctx->comm, st), "ncclAllReduce(G)");
-        return true;
+        return false;
     }
     // sufficient statistics of the row update: G = V V' (:332), B = (M o Y) V', D_k = complement Grams
     { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st); }
@@ -658,16 +683,18 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             s->d_splits = std::min(s->d_splits, std::max(1, g.WPr));
             s->Dp = s->pool.get<double>((size_t)s->d_splits * g.N * KK, true, st);
             s->GLp = s->pool.get<double>((size_t)std::max(1, s->total_levels) * s->max_chunks * KK, true, st);
-            { const char* e = getenv("INSIDER_B200_MASKED_V6"); s->masked_v6 = e && e[0] == '1'; }
+            { const char* e = getenv("INSIDER_B200_MASKED_TILES"); s->masked_v6 = !(e && e[0] == '1'); }
             if (o->alpha == 0.0 || s->masked_v6) s->XtXall = s->pool.get<double>((size_t)std::max<int64_t>(1, g.P) * KK, true, st);
             else s->gram_tiles = s->pool.get<double>(cd_masked_tile_doubles(g.K, std::max<int64_t>(1, g.P)), false, st);
         } else {
             s->GLp = s->pool.get<double>(1, true, st);
         }
         if (r->inc_continuous) s->cont_scratch = s->pool.get<double>(continuous_scratch_elems(g), true, st);
-        s->dense_fast = !s->masked && r->C > 0 && !r->inc_continuous && row_b_levels_supported(g) && !getenv("INSIDER_B200_NO_FAST_CHAIN") &&
+        s->dense_fast = !s->masked && r->C > 0 && !r->inc_continuous && row_b_levels_supported(g, s->total_levels, g.N * r->C) && !getenv("INSIDER_B200_NO_FAST_CHAIN") &&
                         rows_dense_gs_can_fuse_u(g, 0, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz);
         if (s->dense_fast) {
+            s->SB = s->pool.get<double>((size_t)s->total_levels * g.KP + KK, true, st);     // [SB | G]: one all-reduce
+            s->G = s->SB + (size_t)s->total_levels * g.KP;
             s->SBp = s->pool.get<double>((size_t)s->rb_splits * s->total_levels * g.KP, true, st);
             s->gv_parts = s->pool.get<double>((size_t)gram_v_parts(std::max<int64_t>(1, g.P)) * KK, true, st);
             s->gv_counter = s->pool.get<unsigned int>(1, true, st);
@@ -709,10 +736,6 @@ insider_session* do_begin(insider_ctx* ctx, insider_resident* r, const insider_f
             CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming));
         }
         upload_factors(s, f);
-        if (s->dense_fast) {                                                   // G = V V' of the initial column factor (:332 of iteration 0)
-            Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, nullptr, st);
-            if (ctx->world > 1) nccl_check(g_nccl.AllReduce(s->G, s->G, (size_t)KK, NCCL_FLOAT64, NCCL_SUM, ctx->comm, st), "ncclAllReduce(G)");
-        }
         // initial row factor and evaluation (:286-289, :320-323)
         { Launch l(s, "k_build_u", 2); launch_build_u(g, r->C, s->designs_dev, r->Q, r->X, r->inc_continuous ? s->A_all + s->a_off[r->C] : nullptr, s->U, s->Ut, s->UtU, st); }
         evaluate(s, true);

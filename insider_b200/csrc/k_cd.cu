@@ -12,6 +12,7 @@
 //     dL_k = (new - old) ((XtX_kk + l2)(new + old)/2 - upper_k) + lambda alpha (|new| - |old|)
 // summed over the sweep: the same quantity without the cancellation of subtracting two O(|r|^2) numbers. The KKT
 // re-admission test (coordinate_descent.cpp:118-119) is |q_e| > alpha lambda for excluded e because beta_e = 0 there.
+// State form: p_k = q_k + beta_k XtX_kk (the "upper" of coordinate_descent.cpp:94) is what the lanes hold - see k_cd_dense.cu.
 // Visit order: counter-based permutation identical to the oracle's mode B.
 //
 // Mapping (k_cd_persistent): 8 lanes per gene, 4 genes per warp, lane li of a group holds q of coordinates li, li+8, li+16,
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     if (!PERGENE) {
         for (int x = tid; x < KP * KP; x += blockDim.x) {
             const int r = x / KP, c = x % KP;
-            Xall_s[r * XLD + c] = (r < K && c < K) ? a.Xsh[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;
+            Xall_s[r * XLD + c] = (r < K && c < K && r != c) ? a.Xsh[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;   // zero diagonal (p form)
         }
         __syncthreads();
     }
@@ -255,7 +256,19 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     inc |= ((bal >> grp_shift) & 0xffu) << (LPG * s);
                     q[s] = xty[s];
                 }
-                // q = X'y - X'X beta   (:79, in covariance form)
+                // group-shared scalars of every coordinate, then the diagonal is zeroed in the shared copy: the solver keeps
+                // p = q + beta * diag (k_cd_dense.cu, "state form"), whose own entry does not move when its coordinate is updated
+#pragma unroll
+                for (int s = 0; s < SL; ++s) {
+                    const int c = s * LPG + li;
+                    const double d = PERGENE ? Xs[c * XLD + c] : ((c < K) ? a.Xsh[(size_t)c * a.xs_r + (size_t)c * a.xs_c] : 0.0);
+                    Bc[c] = beta[s]; DRc[2 * c] = 0.5 * (d + l2); DRc[2 * c + 1] = 1.0 / (d + l2);
+                }
+                __syncwarp(gmask);
+#pragma unroll
+                for (int s = 0; s < SL; ++s) if (PERGENE) Xs[(s * LPG + li) * XLD + s * LPG + li] = 0.0;
+                __syncwarp(gmask);
+                // p = X'y - (X'X - diag) beta   (:79, in covariance form)
 #pragma unroll
                 for (int ms = 0; ms < SL; ++ms)
                     for (int ml = 0; ml < LPG; ++ml) {
@@ -266,12 +279,6 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                             for (int s = 0; s < SL; ++s) q[s] = fma(-Xs[m * XLD + s * LPG + li], bm, q[s]);
                         }
                     }
-#pragma unroll
-                for (int s = 0; s < SL; ++s) {
-                    const int c = s * LPG + li;
-                    const double d = Xs[c * XLD + c];
-                    Bc[c] = beta[s]; DRc[2 * c] = d; DRc[2 * c + 1] = 1.0 / (d + l2);
-                }
                 __syncwarp(gmask);
                 n_inc = __popc(inc); draw = 0; sweeps = 0; active = true; row_draw = 0xffffffffu;
             }
@@ -304,24 +311,20 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
             double xr[SL];
 #pragma unroll
             for (int s = 0; s < SL; ++s) xr[s] = Xs[k * XLD + s * LPG + li];
-            const double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);            // XtX_kk, 1/(XtX_kk + l2)
+            const double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);            // (XtX_kk + l2) / 2, 1 / (XtX_kk + l2)
             const double bo = Bc[k];
             double qsel = q[0];
 #pragma unroll
             for (int s = 1; s < SL; ++s) qsel = (sk == s) ? q[s] : qsel;
-            const double qk = __shfl_sync(FULL, qsel, ok, LPG);
+            const double up = __shfl_sync(FULL, qsel, ok, LPG);                           // :94 - the state is the upper itself (p form)
             const bool on = (incs >> k) & 1u;
-            const double den = dr.x + l2;
-            const double up = fma(bo, dr.x, qk);                                          // :94
             const double t1 = fabs(up) - la;
-            const double num = copysign(t1, up);
-            double nb = num * dr.y;                                                       // :99-104, correctly rounded num / den
-            nb = fma(fma(-den, nb, num), dr.y, nb);
+            double nb = copysign(t1, up) * dr.y;                                          // :99-104
             nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
             nb = on ? nb : bo;                                                            // excluded coordinate / idle group: no-op
             const double dlt = nb - bo;
             // exact loss decrement: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
-            dl = fma(dlt, fma(0.5 * den, nb + bo, -up), dl);
+            dl = fma(dlt, fma(dr.x, nb + bo, -up), dl);
             dl = fma(la, fabs(nb) - fabs(bo), dl);
             if (li == ok) Bc[k] = nb;                                                     // :106-109
             const double nd = -dlt;

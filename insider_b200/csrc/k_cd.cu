@@ -24,6 +24,7 @@
 // wavefronts per 4 gene-steps; the previous version (position layout re-built through shared memory every sweep, gathers of
 // permuted columns) spent 31 (profiles/r01_ncu_k_cd_persistent_v5_dense_A.txt).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -40,6 +41,12 @@ constexpr int MAX_SWEEPS = 200000;
 __device__ __forceinline__ double grp_sum(double v) {
     v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 1);
     return v;
+}
+// c ? a : b as one selp (kept opaque: nvcc otherwise turns a select chain over q[] into a dynamically indexed local array)
+__device__ __forceinline__ double selp64(double a, double b, int c) {
+    double r;
+    asm("{\n .reg .pred p;\n setp.ne.s32 p, %3, 0;\n selp.f64 %0, %1, %2, p;\n}\n" : "=d"(r) : "d"(a), "d"(b), "r"(c));
+    return r;
 }
 __device__ __forceinline__ double lds64(uint32_t addr) {
     double v;
@@ -164,7 +171,11 @@ struct CdArgs {
 };
 
 // persistent elastic-net solver: every 8-lane group repeatedly claims a gene, solves it, writes it back
-template <int SL, bool PERGENE>
+// LA ("look-ahead", round 2): the upper of the NEXT coordinate is fetched from its owner lane before this step's update is known
+// (the shuffle overlaps the soft-threshold chain) and brought up to date by every lane with one FMA on X[k][k_next] - bitwise the
+// FMA its owner applies. The chain between consecutive steps is then |p| - la -> copysign -> * 1/den -> two selects -> new - old
+// -> FMA: no shuffle, no select, no shared-memory load (the operands of step i + 1 are loaded during step i).
+template <int SL, bool PERGENE, int LA>
 __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KP = SL * LPG;
@@ -205,6 +216,9 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     double q[SL];                                              // q = X'y - X'X beta of coordinates s*8 + li
 #pragma unroll
     for (int s = 0; s < SL; ++s) q[s] = 0.0;
+    double bq[SL];                                             // LA == 2: beta of the same coordinates (otherwise beta lives in Bc)
+#pragma unroll
+    for (int s = 0; s < SL; ++s) bq[s] = 0.0;
 
     while (true) {
         // ---- claim and set up a new gene (divergent per group; group-local masks only)
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     const int c = s * LPG + li;
                     const double d = PERGENE ? Xs[c * XLD + c] : ((c < K) ? a.Xsh[(size_t)c * a.xs_r + (size_t)c * a.xs_c] : 0.0);
                     Bc[c] = beta[s]; DRc[2 * c] = 0.5 * (d + l2); DRc[2 * c + 1] = 1.0 / (d + l2);
+                    bq[s] = beta[s];
                 }
                 __syncwarp(gmask);
 #pragma unroll
@@ -303,6 +318,67 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         // ---- one sweep: step i visits coordinate k = ord[i] of every group (groups are at different sweeps: k differs per group)
         const uint32_t incs = active ? inc : 0u;                                          // finished / retired groups: all steps are no-ops
         double dl = 0.0;
+        if constexpr (LA != 0) {
+            // the group's order row in registers: step i is fully unrolled (compile-time byte positions), so nothing on the way to
+            // the next shuffle or the next operand address waits for a shared-memory load
+            uint32_t ow[2 * SL];
+#pragma unroll
+            for (int w = 0; w < 2 * SL; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s)[w];
+            auto ob = [&](int i) -> int { return (int)((ow[i >> 2] >> (8 * (i & 3))) & 0xffu); };
+            int k = ob(0), kn = (1 < K) ? ob(1) : ob(0);                                      // (K == KP - 7 == 1 is possible)
+            double xr[SL];
+#pragma unroll
+            for (int s = 0; s < SL; ++s) xr[s] = Xs[k * XLD + s * LPG + li];
+            double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);
+            double bo = Bc[k], xkn = Xs[k * XLD + kn];
+            double up;
+            {
+                double qsel = q[0], bsel = bq[0];
+#pragma unroll
+                for (int s = 1; s < SL; ++s) { qsel = selp64(q[s], qsel, (k >> 3) == s); bsel = selp64(bq[s], bsel, (k >> 3) == s); }
+                up = __shfl_sync(FULL, qsel, k & 7, LPG);
+                if (LA == 2) bo = __shfl_sync(FULL, bsel, k & 7, LPG);
+            }
+#pragma unroll
+            for (int i = 0; i < KP; ++i) {
+                if (i >= KP - 7 && i >= K) break;                                             // KP - 7 <= K <= KP: the first KP - 7 steps always run
+                const int knn = (i + 2 < KP && (i + 2 < KP - 7 || i + 2 < K)) ? ob((i + 2 < KP) ? i + 2 : KP - 1) : kn;
+                // operands of step i + 1 (addresses depend on the order only) and its upper as of BEFORE this step's update
+                double xrn[SL];
+#pragma unroll
+                for (int s = 0; s < SL; ++s) xrn[s] = Xs[kn * XLD + s * LPG + li];
+                const double2 drn = *reinterpret_cast<const double2*>(DRc + 2 * kn);
+                const double xknn = Xs[kn * XLD + knn];
+                double qsel = q[0], bsel = bq[0];
+#pragma unroll
+                for (int s = 1; s < SL; ++s) { qsel = selp64(q[s], qsel, (kn >> 3) == s); if (LA == 2) bsel = selp64(bq[s], bsel, (kn >> 3) == s); }
+                const double shn = __shfl_sync(FULL, qsel, kn & 7, LPG);
+                // beta of k_next: LA == 2 keeps beta in its owner's registers (no shared-memory store in the sweep: nothing orders
+                // the operand loads behind a store they might alias), LA == 1 in the group's shared array
+                double bon;
+                if (LA == 2) bon = __shfl_sync(FULL, bsel, kn & 7, LPG); else bon = Bc[kn];
+                // the step itself (coordinate_descent.cpp:94-109)
+                const bool on = (incs >> k) & 1u;
+                const double t1 = fabs(up) - la;
+                double nb = copysign(t1, up) * dr.y;
+                nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
+                nb = on ? nb : bo;
+                const double dlt = nb - bo;
+                const double nd = -dlt;
+                const double upn = fma(nd, xkn, shn);                                         // what the owner of k_next computes below
+#pragma unroll
+                for (int s = 0; s < SL; ++s) q[s] = fma(nd, xr[s], q[s]);
+                if (LA == 2) {
+#pragma unroll
+                    for (int s = 0; s < SL; ++s) bq[s] = selp64(nb, bq[s], (li == (k & 7)) && ((k >> 3) == s));
+                } else if (li == (k & 7)) Bc[k] = nb;
+                dl = fma(dlt, fma(dr.x, nb + bo, -up), dl);
+                dl = fma(la, fabs(nb) - fabs(bo), dl);
+                k = kn; kn = knn; dr = drn; bo = bon; xkn = xknn; up = upn;
+#pragma unroll
+                for (int s = 0; s < SL; ++s) xr[s] = xrn[s];
+            }
+        } else {
         int k = ord_s[0];
         for (int i = 0; i < K; ++i) {
             const int kn = ord_s[(i + 1 < K) ? i + 1 : i];
@@ -332,6 +408,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
             for (int s = 0; s < SL; ++s) q[s] = fma(nd, xr[s], q[s]);
             k = kn;
         }
+        }
         __syncwarp();
         // inner do-while ends (:114) -> KKT check on the excluded set (:118-124); every lane of the group holds the same dl
         const bool inner_end = active && (!(fabs(dl) > tol) || sweeps + 1 >= MAX_SWEEPS);
@@ -343,7 +420,9 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 if (c < K && !((inc >> c) & 1u) && fabs(q[s]) > la) vmask |= 1u << c;     // |XtX[e,inc] beta - Xty_e| = |q_e| (beta_e = 0)
             }
         }
-        vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
+        if (__any_sync(FULL, inner_end)) {                                                // (most sweeps end nowhere: one vote instead of three shuffles)
+            vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
+        }
         if (active) {
             ++sweeps;
             steps_acc += (unsigned long long)n_inc;     // coordinate updates attempted (statistics only)
@@ -351,7 +430,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 if (vmask == 0u || sweeps >= MAX_SWEEPS) {
                     // finished: write the gene back
 #pragma unroll
-                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = Bc[c]; }
+                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = (LA == 2) ? bq[s] : Bc[c]; }
                     if (li == 0) { sweeps_acc += (unsigned long long)sweeps; if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps; }
                     active = false;
                 } else { inc |= vmask; n_inc = __popc(inc); }
@@ -433,10 +512,13 @@ void launch_cd(const CdArgs& a, int KP, bool pergene, int sm_count, cudaStream_t
     if (per_sm < 1) per_sm = 1;
     blocks = std::min<int64_t>(blocks, (int64_t)sm_count * per_sm);
     cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), st);
-#define LAUNCH_CD(SLv)                                                                                                      \
-    if (pergene) { opt_in_smem(k_cd_persistent<SLv, true>, smem); k_cd_persistent<SLv, true><<<(int)blocks, CD_WARPS * 32, smem, st>>>(a); } \
-    else { opt_in_smem(k_cd_persistent<SLv, false>, smem); k_cd_persistent<SLv, false><<<(int)blocks, CD_WARPS * 32, smem, st>>>(a); }
+    static const int la = [] { const char* e = getenv("INSIDER_B200_CD_LA"); return e ? atoi(e) : 1; }();      // A/B switch (profiles/r02_*): 0 round-1 step
+#define LAUNCH_CD1(SLv, PG, LAv) { opt_in_smem(k_cd_persistent<SLv, PG, LAv>, smem); k_cd_persistent<SLv, PG, LAv><<<(int)blocks, CD_WARPS * 32, smem, st>>>(a); }
+#define LAUNCH_CD2(SLv, PG) { if (la == 0) LAUNCH_CD1(SLv, PG, 0) else if (la == 1) LAUNCH_CD1(SLv, PG, 1) else LAUNCH_CD1(SLv, PG, 2) }
+#define LAUNCH_CD(SLv) { if (pergene) LAUNCH_CD2(SLv, true) else LAUNCH_CD2(SLv, false) }
     switch (KP / 8) { case 1: LAUNCH_CD(1) break; case 2: LAUNCH_CD(2) break; case 3: LAUNCH_CD(3) break; default: LAUNCH_CD(4) break; }
+#undef LAUNCH_CD2
+#undef LAUNCH_CD1
 #undef LAUNCH_CD
 }
 

@@ -565,7 +565,8 @@ void run_column_update(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
     insider_resident* r = s->r;
     const Geom& g = s->g;
-    const bool dense_cd = !s->masked && s->opt.alpha != 0.0;
+    static const bool dense_group = getenv("INSIDER_B200_DENSE_GROUP") != nullptr;   // A/B: 8-lanes-per-gene solver on the dense path
+    const bool dense_cd = !s->masked && s->opt.alpha != 0.0 && !dense_group;
     SideSection sec1(s, 1);                // dense elastic net: slot order and XtX table (neither needs Xty) beside the pass over Y
     if (dense_cd) {
         { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, sec1.side); }
@@ -607,10 +608,11 @@ void run_column_update(insider_session* s) {
         launch_cd_dense(g, s->UtU, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->sweeps_gene, s->cd_order, s->ctx->perm_table, s->cd_table,
                         s->graph_variant == 2, nullptr, 0u, 0xffffffffu, s->graph_variant < 2 ? s->cd_tables_all : nullptr, st);
     } else {
-        if (masked_cd) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
+        const bool group_cd = s->opt.alpha != 0.0;
+        if (group_cd) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count,
-                         masked_cd ? s->sweeps_gene : nullptr, masked_cd ? s->cd_order : nullptr, st);
+                         group_cd ? s->sweeps_gene : nullptr, group_cd ? s->cd_order : nullptr, st);
     }
 }
 

@@ -33,8 +33,6 @@ namespace ib {
 
 namespace {
 
-constexpr int LPG = 8;            // lanes per gene
-constexpr int GPW = 4;            // genes per warp
 constexpr int CD_WARPS = 2;       // warps per block (8 genes, 43 KB of per-gene tables at K = 23: 5 blocks = 40 genes per SM)
 constexpr int MAX_SWEEPS = 200000;
 
@@ -170,28 +168,47 @@ struct CdArgs {
     const unsigned char* perm_table;   // rank + order tables (common.cuh)
 };
 
-// persistent elastic-net solver: every 8-lane group repeatedly claims a gene, solves it, writes it back
-// LA ("look-ahead", round 2): the upper of the NEXT coordinate is fetched from its owner lane before this step's update is known
-// (the shuffle overlaps the soft-threshold chain) and brought up to date by every lane with one FMA on X[k][k_next] - bitwise the
-// FMA its owner applies. The chain between consecutive steps is then |p| - la -> copysign -> * 1/den -> two selects -> new - old
-// -> FMA: no shuffle, no select, no shared-memory load (the operands of step i + 1 are loaded during step i).
-template <int SL, bool PERGENE, int LA>
-__global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
+// persistent elastic-net solver: every LPG-lane group repeatedly claims a gene, solves it, writes it back.
+//
+// Step (round 2, "look-ahead"): the upper of the NEXT coordinate is fetched from its owner lane before this step's update is
+// known (the shuffle overlaps the soft-threshold chain) and brought up to date by every lane with one FMA on X[k][k_next] -
+// bitwise the FMA its owner applies. The chain between consecutive steps is |p| - la -> copysign -> * 1/den -> two selects ->
+// new - old -> FMA: no shuffle, no select, no shared-memory load on it (the operands of step i + 1 are loaded during step i;
+// the order row sits in registers and the sweep is fully unrolled, so operand addresses never wait for a load either).
+// Measured (profiles/r02_masked_solver_versions.txt): first 13 masked iterations 237 -> 202 ms, lone-warp sweep 2.45 -> 1.59 us.
+//
+// Matrix layout in shared memory (round 2): row r is SL lines of 16 doubles; a line holds LPG consecutive columns of 16 / LPG
+// genes (neighbouring groups of a warp) side by side: element (r, c) of gene slot h at (r*SL + c/LPG)*16 + h*LPG + c%LPG. The
+// groups of a warp read rows of different matrices at every step; the groups served in one half-warp phase of an LDS.64 sit in
+// disjoint bank ranges whatever their rows are (rows of pitch KP + 1 started at arbitrary banks: 30 % of the wavefronts were
+// conflicts, profiles/r02_ncu_k_cd_persistent_la_masked.txt).
+template <int LPGv> struct GroupGeom {
+    static constexpr int LPG = LPGv, GPW = 32 / LPGv, LOG = (LPGv == 8) ? 3 : 2, GPL = 16 / LPGv;
+    static constexpr int WARPS = (LPGv == 8) ? CD_WARPS : 1;      // 8 genes (41.7 KB of tables at K = 23) per block either way
+    static constexpr int OW = 8 / LPGv;                           // 32-bit words of the 32-byte order row per lane
+};
+
+template <int KP, int LPGv, bool PERGENE>
+__global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(CdArgs a) {
+    using GG = GroupGeom<LPGv>;
+    constexpr int LPG = GG::LPG, GPW = GG::GPW, LOG = GG::LOG, GPL = GG::GPL, NWARP = GG::WARPS, OW = GG::OW;
+    constexpr int SL = KP / LPG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int KP = SL * LPG;
-    constexpr int XLD = KP + 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, li = lane & 7;
-    const int grp_shift = grp << 3;
-    const uint32_t gmask = 0xffu << grp_shift;
+    constexpr int MAT = KP * SL * 16;                                          // doubles per GPL interleaved matrices
+    auto XI = [](int r, int c) -> int { return (r * SL + (c >> LOG)) * 16 + (c & (LPG - 1)); };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> LOG, li = lane & (LPG - 1);
+    const int grp_shift = grp << LOG;
+    constexpr uint32_t lmask = (1u << LPG) - 1u;
+    const uint32_t gmask = lmask << grp_shift;
     double* Xall_s = reinterpret_cast<double*>(smem_raw);
-    constexpr int n_mats = PERGENE ? CD_WARPS * GPW : 1;
-    double* sh_all = Xall_s + (size_t)n_mats * KP * XLD;                       // [CD_WARPS*GPW][3*KP]
-    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)CD_WARPS * GPW * 3 * KP);
+    constexpr int n_mats = PERGENE ? NWARP * GPW : 1;
+    double* sh_all = Xall_s + (size_t)((n_mats + GPL - 1) / GPL) * MAT;        // [NWARP*GPW][3*KP]
+    unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)NWARP * GPW * 3 * KP);
     const int gslot = warp * GPW + grp;
-    double* Xs = PERGENE ? Xall_s + (size_t)gslot * KP * XLD : Xall_s;
+    double* Xs = PERGENE ? Xall_s + (size_t)(gslot / GPL) * MAT + (gslot % GPL) * LPG : Xall_s;
     double* sh = sh_all + (size_t)gslot * 3 * KP;
     unsigned char* ord_s = ord_all + gslot * 32;
-    double* Bc = sh; double* DRc = sh + KP;            // beta [KP] | (XtX_kk, 1/(XtX_kk + l2)) pairs [2*KP]   (16-byte aligned: KP % 8 == 0)
+    double* Bc = sh; double* DRc = sh + KP;            // beta [KP] | ((XtX_kk + l2)/2, 1/(XtX_kk + l2)) pairs [2*KP]   (16-byte aligned: KP % 8 == 0)
     const int K = a.K;
     const double tol = a.tol_dev ? *a.tol_dev : a.tol_host;
     const uint32_t als_iter = a.als_iter_dev ? *a.als_iter_dev : a.als_iter_host;
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     if (!PERGENE) {
         for (int x = tid; x < KP * KP; x += blockDim.x) {
             const int r = x / KP, c = x % KP;
-            Xall_s[r * XLD + c] = (r < K && c < K && r != c) ? a.Xsh[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;   // zero diagonal (p form)
+            Xall_s[XI(r, c)] = (r < K && c < K && r != c) ? a.Xsh[(size_t)r * a.xs_r + (size_t)c * a.xs_c] : 0.0;   // zero diagonal (p form)
         }
         __syncthreads();
     }
@@ -211,14 +228,13 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
     bool active = false, retired = false;
     uint32_t inc = 0, draw = 0;
     int n_inc = 0, sweeps = 0;
-    uint32_t row_w = 0, row_draw = 0xffffffffu;                // prefetched order-table word (see below)
+    uint32_t row_w[OW], row_draw = 0xffffffffu;                // prefetched order-table words (see below)
+#pragma unroll
+    for (int w = 0; w < OW; ++w) row_w[w] = 0;
     unsigned long long sweeps_acc = 0, steps_acc = 0;
-    double q[SL];                                              // q = X'y - X'X beta of coordinates s*8 + li
+    double q[SL];                                              // p = X'y - (X'X - diag) beta of coordinates s*LPG + li
 #pragma unroll
     for (int s = 0; s < SL; ++s) q[s] = 0.0;
-    double bq[SL];                                             // LA == 2: beta of the same coordinates (otherwise beta lives in Bc)
-#pragma unroll
-    for (int s = 0; s < SL; ++s) bq[s] = 0.0;
 
     while (true) {
         // ---- claim and set up a new gene (divergent per group; group-local masks only)
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 gene = a.order ? (int64_t)a.order[jn] : (int64_t)jn;
                 if (PERGENE) {
                     // per-gene matrix global -> shared, eight independent loads in flight per lane (a plain strided loop
-                    // pays one L2 round trip per element: 72 of them per gene)
+                    // pays one L2 round trip per element)
                     const double* src = a.Xall + (size_t)gene * a.x_stride;
                     for (int x0 = li; x0 < KP * KP; x0 += 8 * LPG) {
                         double v[8];
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int x = x0 + u * LPG;
-                            if (x < KP * KP) Xs[(x / KP) * XLD + (x % KP)] = v[u];
+                            if (x < KP * KP) Xs[XI(x / KP, x % KP)] = v[u];
                         }
                     }
                     __syncwarp(gmask);
@@ -258,7 +274,8 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     beta[s] = (c < K) ? a.W0[gene * a.ldv + c] : 0.0;
                     mx = fmax(mx, fabs(xty[s]));
                 }
-                mx = fmax(mx, __shfl_xor_sync(gmask, mx, 4)); mx = fmax(mx, __shfl_xor_sync(gmask, mx, 2)); mx = fmax(mx, __shfl_xor_sync(gmask, mx, 1));
+#pragma unroll
+                for (int o = LPG / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(gmask, mx, o));
                 const double thr = a.alpha * (2.0 * a.lambda - mx);                // coordinate_descent.cpp:74
                 inc = 0;
 #pragma unroll
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                     const bool on = (c < K) && !(fabs(xty[s]) < thr);
                     if (!on) beta[s] = 0.0;                                        // :75-78
                     const uint32_t bal = __ballot_sync(gmask, on);
-                    inc |= ((bal >> grp_shift) & 0xffu) << (LPG * s);
+                    inc |= ((bal >> grp_shift) & lmask) << (LPG * s);
                     q[s] = xty[s];
                 }
                 // group-shared scalars of every coordinate, then the diagonal is zeroed in the shared copy: the solver keeps
@@ -275,13 +292,12 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
 #pragma unroll
                 for (int s = 0; s < SL; ++s) {
                     const int c = s * LPG + li;
-                    const double d = PERGENE ? Xs[c * XLD + c] : ((c < K) ? a.Xsh[(size_t)c * a.xs_r + (size_t)c * a.xs_c] : 0.0);
+                    const double d = PERGENE ? Xs[XI(c, c)] : ((c < K) ? a.Xsh[(size_t)c * a.xs_r + (size_t)c * a.xs_c] : 0.0);
                     Bc[c] = beta[s]; DRc[2 * c] = 0.5 * (d + l2); DRc[2 * c + 1] = 1.0 / (d + l2);
-                    bq[s] = beta[s];
                 }
                 __syncwarp(gmask);
 #pragma unroll
-                for (int s = 0; s < SL; ++s) if (PERGENE) Xs[(s * LPG + li) * XLD + s * LPG + li] = 0.0;
+                for (int s = 0; s < SL; ++s) if (PERGENE) Xs[XI(s * LPG + li, s * LPG + li)] = 0.0;
                 __syncwarp(gmask);
                 // p = X'y - (X'X - diag) beta   (:79, in covariance form)
 #pragma unroll
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                         const double bm = __shfl_sync(gmask, beta[ms], ml, LPG);
                         if (m < K && bm != 0.0) {
 #pragma unroll
-                            for (int s = 0; s < SL; ++s) q[s] = fma(-Xs[m * XLD + s * LPG + li], bm, q[s]);
+                            for (int s = 0; s < SL; ++s) q[s] = fma(-Xs[(m * SL + s) * 16 + li], bm, q[s]);
                         }
                     }
                 __syncwarp(gmask);
@@ -302,43 +318,46 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
 
         // ---- visiting order of this group's sweep (coordinate_descent.cpp:89): the per-sweep key selects a table permutation of
         //      all K coordinates (shared by every gene at this sweep index); active coordinates are visited in that order. Lane
-        //      li holds 4-byte word li of the 32-byte order row; the row of the NEXT sweep is prefetched one sweep ahead.
+        //      li holds the 4-byte words li, li + LPG, .. of the 32-byte order row; the row of the NEXT sweep is prefetched one
+        //      sweep ahead.
         {
-            auto row_word = [&](uint32_t dr) -> uint32_t {
-                if (a.perm_mode != 1) { const uint32_t c0 = 4u * li; return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24); }
+            auto row_word = [&](uint32_t dr, int w) -> uint32_t {
+                const uint32_t wi = (uint32_t)(li + w * LPG);
+                if (a.perm_mode != 1) { const uint32_t c0 = 4u * wi; return c0 | ((c0 + 1) << 8) | ((c0 + 2) << 16) | ((c0 + 3) << 24); }
                 const uint64_t pk = key_iter ^ mix64((uint64_t)dr * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull);
-                return __ldg(reinterpret_cast<const uint32_t*>(a.perm_table + PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + li);
+                return __ldg(reinterpret_cast<const uint32_t*>(a.perm_table + PERM_TABLE_HALF + ((size_t)(K - 1) * PERM_T + perm_select(pk)) * 32) + wi);
             };
-            if (row_draw != draw) row_w = row_word(draw);                                 // new gene
-            reinterpret_cast<uint32_t*>(ord_s)[li] = row_w;
-            row_w = row_word(draw + 1); row_draw = draw + 1;                              // consumed by the next sweep
+#pragma unroll
+            for (int w = 0; w < OW; ++w) {
+                if (row_draw != draw) row_w[w] = row_word(draw, w);                       // new gene
+                reinterpret_cast<uint32_t*>(ord_s)[li + w * LPG] = row_w[w];
+                row_w[w] = row_word(draw + 1, w);                                         // consumed by the next sweep
+            }
+            row_draw = draw + 1;
         }
         ++draw;
         __syncwarp();
         // ---- one sweep: step i visits coordinate k = ord[i] of every group (groups are at different sweeps: k differs per group)
         const uint32_t incs = active ? inc : 0u;                                          // finished / retired groups: all steps are no-ops
         double dl = 0.0;
-        if constexpr (LA != 0) {
-            // the group's order row in registers: step i is fully unrolled (compile-time byte positions), so nothing on the way to
-            // the next shuffle or the next operand address waits for a shared-memory load
-            uint32_t ow[2 * SL];
+        {
+            uint32_t ow[KP / 4];
 #pragma unroll
-            for (int w = 0; w < 2 * SL; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s)[w];
+            for (int w = 0; w < KP / 4; ++w) ow[w] = reinterpret_cast<const uint32_t*>(ord_s)[w];
             auto ob = [&](int i) -> int { return (int)((ow[i >> 2] >> (8 * (i & 3))) & 0xffu); };
+            auto sel_slot = [&](int kk) -> double {                                       // q of coordinate kk in its owner lane
+                double v = q[0];
+#pragma unroll
+                for (int s = 1; s < SL; ++s) v = selp64(q[s], v, (kk >> LOG) == s);
+                return v;
+            };
             int k = ob(0), kn = (1 < K) ? ob(1) : ob(0);                                      // (K == KP - 7 == 1 is possible)
             double xr[SL];
 #pragma unroll
-            for (int s = 0; s < SL; ++s) xr[s] = Xs[k * XLD + s * LPG + li];
-            double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);
-            double bo = Bc[k], xkn = Xs[k * XLD + kn];
-            double up;
-            {
-                double qsel = q[0], bsel = bq[0];
-#pragma unroll
-                for (int s = 1; s < SL; ++s) { qsel = selp64(q[s], qsel, (k >> 3) == s); bsel = selp64(bq[s], bsel, (k >> 3) == s); }
-                up = __shfl_sync(FULL, qsel, k & 7, LPG);
-                if (LA == 2) bo = __shfl_sync(FULL, bsel, k & 7, LPG);
-            }
+            for (int s = 0; s < SL; ++s) xr[s] = Xs[(k * SL + s) * 16 + li];
+            double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);                  // (XtX_kk + l2) / 2, 1 / (XtX_kk + l2)
+            double bo = Bc[k], xkn = Xs[XI(k, kn)];
+            double up = __shfl_sync(FULL, sel_slot(k), k & (LPG - 1), LPG);               // :94 - the state is the upper itself (p form)
 #pragma unroll
             for (int i = 0; i < KP; ++i) {
                 if (i >= KP - 7 && i >= K) break;                                             // KP - 7 <= K <= KP: the first KP - 7 steps always run
@@ -346,68 +365,30 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 // operands of step i + 1 (addresses depend on the order only) and its upper as of BEFORE this step's update
                 double xrn[SL];
 #pragma unroll
-                for (int s = 0; s < SL; ++s) xrn[s] = Xs[kn * XLD + s * LPG + li];
+                for (int s = 0; s < SL; ++s) xrn[s] = Xs[(kn * SL + s) * 16 + li];
                 const double2 drn = *reinterpret_cast<const double2*>(DRc + 2 * kn);
-                const double xknn = Xs[kn * XLD + knn];
-                double qsel = q[0], bsel = bq[0];
-#pragma unroll
-                for (int s = 1; s < SL; ++s) { qsel = selp64(q[s], qsel, (kn >> 3) == s); if (LA == 2) bsel = selp64(bq[s], bsel, (kn >> 3) == s); }
-                const double shn = __shfl_sync(FULL, qsel, kn & 7, LPG);
-                // beta of k_next: LA == 2 keeps beta in its owner's registers (no shared-memory store in the sweep: nothing orders
-                // the operand loads behind a store they might alias), LA == 1 in the group's shared array
-                double bon;
-                if (LA == 2) bon = __shfl_sync(FULL, bsel, kn & 7, LPG); else bon = Bc[kn];
+                const double xknn = Xs[XI(kn, knn)];
+                const double shn = __shfl_sync(FULL, sel_slot(kn), kn & (LPG - 1), LPG);
+                const double bon = Bc[kn];
                 // the step itself (coordinate_descent.cpp:94-109)
                 const bool on = (incs >> k) & 1u;
                 const double t1 = fabs(up) - la;
-                double nb = copysign(t1, up) * dr.y;
+                double nb = copysign(t1, up) * dr.y;                                          // :99-104
                 nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
-                nb = on ? nb : bo;
+                nb = on ? nb : bo;                                                            // excluded coordinate / idle group: no-op
                 const double dlt = nb - bo;
                 const double nd = -dlt;
                 const double upn = fma(nd, xkn, shn);                                         // what the owner of k_next computes below
 #pragma unroll
                 for (int s = 0; s < SL; ++s) q[s] = fma(nd, xr[s], q[s]);
-                if (LA == 2) {
-#pragma unroll
-                    for (int s = 0; s < SL; ++s) bq[s] = selp64(nb, bq[s], (li == (k & 7)) && ((k >> 3) == s));
-                } else if (li == (k & 7)) Bc[k] = nb;
+                if (li == (k & (LPG - 1))) Bc[k] = nb;                                        // :106-109
+                // exact loss decrement: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
                 dl = fma(dlt, fma(dr.x, nb + bo, -up), dl);
                 dl = fma(la, fabs(nb) - fabs(bo), dl);
                 k = kn; kn = knn; dr = drn; bo = bon; xkn = xknn; up = upn;
 #pragma unroll
                 for (int s = 0; s < SL; ++s) xr[s] = xrn[s];
             }
-        } else {
-        int k = ord_s[0];
-        for (int i = 0; i < K; ++i) {
-            const int kn = ord_s[(i + 1 < K) ? i + 1 : i];
-            const int sk = k >> 3, ok = k & 7;
-            // the gene's row k (8 consecutive doubles per slot and group) and the group's scalars of coordinate k
-            double xr[SL];
-#pragma unroll
-            for (int s = 0; s < SL; ++s) xr[s] = Xs[k * XLD + s * LPG + li];
-            const double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);            // (XtX_kk + l2) / 2, 1 / (XtX_kk + l2)
-            const double bo = Bc[k];
-            double qsel = q[0];
-#pragma unroll
-            for (int s = 1; s < SL; ++s) qsel = (sk == s) ? q[s] : qsel;
-            const double up = __shfl_sync(FULL, qsel, ok, LPG);                           // :94 - the state is the upper itself (p form)
-            const bool on = (incs >> k) & 1u;
-            const double t1 = fabs(up) - la;
-            double nb = copysign(t1, up) * dr.y;                                          // :99-104
-            nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
-            nb = on ? nb : bo;                                                            // excluded coordinate / idle group: no-op
-            const double dlt = nb - bo;
-            // exact loss decrement: dlt ((XtX_kk + l2)(new + old)/2 - upper) + lambda alpha (|new| - |old|)
-            dl = fma(dlt, fma(dr.x, nb + bo, -up), dl);
-            dl = fma(la, fabs(nb) - fabs(bo), dl);
-            if (li == ok) Bc[k] = nb;                                                     // :106-109
-            const double nd = -dlt;
-#pragma unroll
-            for (int s = 0; s < SL; ++s) q[s] = fma(nd, xr[s], q[s]);
-            k = kn;
-        }
         }
         __syncwarp();
         // inner do-while ends (:114) -> KKT check on the excluded set (:118-124); every lane of the group holds the same dl
@@ -420,8 +401,9 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 if (c < K && !((inc >> c) & 1u) && fabs(q[s]) > la) vmask |= 1u << c;     // |XtX[e,inc] beta - Xty_e| = |q_e| (beta_e = 0)
             }
         }
-        if (__any_sync(FULL, inner_end)) {                                                // (most sweeps end nowhere: one vote instead of three shuffles)
-            vmask |= __shfl_xor_sync(FULL, vmask, 4); vmask |= __shfl_xor_sync(FULL, vmask, 2); vmask |= __shfl_xor_sync(FULL, vmask, 1);
+        if (__any_sync(FULL, inner_end)) {                                                // (most sweeps end nowhere: one vote instead of the shuffles)
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) vmask |= __shfl_xor_sync(FULL, vmask, o);
         }
         if (active) {
             ++sweeps;
@@ -430,7 +412,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
                 if (vmask == 0u || sweeps >= MAX_SWEEPS) {
                     // finished: write the gene back
 #pragma unroll
-                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = (LA == 2) ? bq[s] : Bc[c]; }
+                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = Bc[c]; }
                     if (li == 0) { sweeps_acc += (unsigned long long)sweeps; if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps; }
                     active = false;
                 } else { inc |= vmask; n_inc = __popc(inc); }
@@ -438,10 +420,10 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_cd_persistent(CdArgs a) {
         }
     }
     // one atomic per warp for the sweep statistics
-    sweeps_acc += __shfl_xor_sync(FULL, sweeps_acc, 8); sweeps_acc += __shfl_xor_sync(FULL, sweeps_acc, 16);
-    if (lane == 0 && sweeps_acc && a.sweeps_total) atomicAdd(a.sweeps_total, sweeps_acc);
     if (li != 0) steps_acc = 0;
-    steps_acc += __shfl_xor_sync(FULL, steps_acc, 8); steps_acc += __shfl_xor_sync(FULL, steps_acc, 16);
+#pragma unroll
+    for (int o = LPG; o < 32; o <<= 1) { sweeps_acc += __shfl_xor_sync(FULL, sweeps_acc, o); steps_acc += __shfl_xor_sync(FULL, steps_acc, o); }
+    if (lane == 0 && sweeps_acc && a.sweeps_total) atomicAdd(a.sweeps_total, sweeps_acc);
     if (lane == 0 && steps_acc && a.steps_total) atomicAdd(a.steps_total, steps_acc);
 }
 
@@ -499,26 +481,38 @@ void opt_in_smem(KernelT k, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+template <int LPGv>
 size_t cd_smem_bytes(int KP, bool pergene) {
-    const size_t mats = pergene ? (size_t)CD_WARPS * GPW : 1;
-    return mats * KP * (KP + 1) * 8 + (size_t)CD_WARPS * GPW * 3 * KP * 8 + CD_WARPS * GPW * 32;
+    using GG = GroupGeom<LPGv>;
+    const size_t genes = (size_t)GG::WARPS * GG::GPW;
+    const size_t sets = pergene ? genes / GG::GPL : 1;                         // 16 / LPG matrices interleaved per 128-byte line
+    return sets * KP * (KP / LPGv) * 16 * 8 + genes * 3 * KP * 8 + genes * 32;
 }
 
-void launch_cd(const CdArgs& a, int KP, bool pergene, int sm_count, cudaStream_t st) {
-    const size_t smem = cd_smem_bytes(KP, pergene);
-    const int64_t genes_per_block = CD_WARPS * GPW;
+template <int KP, int LPGv, bool PG>
+void launch_cd_kp(const CdArgs& a, int sm_count, cudaStream_t st) {
+    using GG = GroupGeom<LPGv>;
+    const size_t smem = cd_smem_bytes<LPGv>(KP, PG);
+    const int64_t genes_per_block = GG::WARPS * GG::GPW;
     int64_t blocks = (a.P + genes_per_block - 1) / genes_per_block;
     int per_sm = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));      // persistent: enough blocks to fill every SM
     if (per_sm < 1) per_sm = 1;
     blocks = std::min<int64_t>(blocks, (int64_t)sm_count * per_sm);
+    opt_in_smem(k_cd_persistent<KP, LPGv, PG>, smem);
+    k_cd_persistent<KP, LPGv, PG><<<(int)blocks, GG::WARPS * 32, smem, st>>>(a);
+}
+
+// long_solves: hundreds of sweeps per gene expected (first ALS iterations). 4 lanes per gene issue 7.8 instead of 13.3 warp
+// instructions per gene-step (8 genes per warp share the scalar chain) and win there (iteration 0: 92 -> 83 ms); 8 lanes per gene
+// set a gene up twice as fast and have the shorter lone-warp sweep (1.6 against 1.95 us): better from ~100 sweeps per gene down.
+void launch_cd(const CdArgs& a, int KP, bool pergene, int sm_count, bool long_solves, cudaStream_t st) {
     cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), st);
-    static const int la = [] { const char* e = getenv("INSIDER_B200_CD_LA"); return e ? atoi(e) : 1; }();      // A/B switch (profiles/r02_*): 0 round-1 step
-#define LAUNCH_CD1(SLv, PG, LAv) { opt_in_smem(k_cd_persistent<SLv, PG, LAv>, smem); k_cd_persistent<SLv, PG, LAv><<<(int)blocks, CD_WARPS * 32, smem, st>>>(a); }
-#define LAUNCH_CD2(SLv, PG) { if (la == 0) LAUNCH_CD1(SLv, PG, 0) else if (la == 1) LAUNCH_CD1(SLv, PG, 1) else LAUNCH_CD1(SLv, PG, 2) }
-#define LAUNCH_CD(SLv) { if (pergene) LAUNCH_CD2(SLv, true) else LAUNCH_CD2(SLv, false) }
-    switch (KP / 8) { case 1: LAUNCH_CD(1) break; case 2: LAUNCH_CD(2) break; case 3: LAUNCH_CD(3) break; default: LAUNCH_CD(4) break; }
-#undef LAUNCH_CD2
-#undef LAUNCH_CD1
+    static const int lpg_env = [] { const char* e = getenv("INSIDER_B200_CD_LPG"); return e ? atoi(e) : 0; }();   // A/B switch (profiles/r02_masked_solver_versions.txt)
+    const int lpg = (lpg_env == 4 || lpg_env == 8) ? lpg_env : (long_solves ? 4 : 8);
+#define LAUNCH_CD(KPv)                                                                                                    \
+    { if (lpg == 8) { if (pergene) launch_cd_kp<KPv, 8, true>(a, sm_count, st); else launch_cd_kp<KPv, 8, false>(a, sm_count, st); }   \
+      else { if (pergene) launch_cd_kp<KPv, 4, true>(a, sm_count, st); else launch_cd_kp<KPv, 4, false>(a, sm_count, st); } }
+    switch (KP / 8) { case 1: LAUNCH_CD(8) break; case 2: LAUNCH_CD(16) break; case 3: LAUNCH_CD(24) break; default: LAUNCH_CD(32) break; }
 #undef LAUNCH_CD
 }
 
@@ -537,7 +531,7 @@ void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const 
 
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
                       unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
-                      int sm_count, int* sweeps_per_gene, const int* order, cudaStream_t st) {
+                      int sm_count, int* sweeps_per_gene, const int* order, bool long_solves, cudaStream_t st) {
     if (g.P == 0) return;
     if (p.alpha == 0.0) {
         RidgeArgs r{UtU, XtXall, Xty, V, g.K, g.KP, g.ldV, g.P, p.lambda, err_flag};
@@ -552,7 +546,7 @@ void launch_col_solve(const Geom& g, bool masked, const double* UtU, const doubl
     a.Xty = Xty; a.W0 = V; a.Vout = V; a.ldv = g.ldV; a.K = g.K; a.P = g.P; a.gene0 = g.gene0;
     a.lambda = p.lambda; a.alpha = p.alpha; a.tol_dev = p.tol; a.als_iter_dev = p.als_iter; a.seed = p.seed; a.perm_mode = p.perm_mode;
     a.sweeps_total = sweeps; a.steps_total = steps; a.sweeps_per_gene = sweeps_per_gene; a.order = order; a.queue = queue; a.perm_table = perm_table;
-    launch_cd(a, g.KP, masked, sm_count, st);
+    launch_cd(a, g.KP, masked, sm_count, long_solves, st);
 }
 
 void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const double* Xty, const double* w0, double lambda, double alpha,
@@ -564,7 +558,7 @@ void launch_cd_batch(int K, int64_t n, const double* XtX, bool shared, const dou
     a.Xty = Xty; a.W0 = w0; a.Vout = beta; a.ldv = K; a.K = K; a.P = n; a.gene0 = (int64_t)gene0;
     a.lambda = lambda; a.alpha = alpha; a.tol_dev = nullptr; a.tol_host = tol; a.als_iter_dev = nullptr; a.als_iter_host = als_iter;
     a.seed = seed; a.perm_mode = perm_mode; a.sweeps_total = nullptr; a.steps_total = nullptr; a.sweeps_per_gene = sweeps; a.queue = queue;
-    launch_cd(a, round_up(K, 8), !shared, sm_count, st);
+    launch_cd(a, round_up(K, 8), !shared, sm_count, false, st);
 }
 
 }  // namespace ib

@@ -120,7 +120,7 @@ void launch_col_gram(const Geom& g, const uint32_t* trC, const double* U, const 
 // on the previous iteration's counts: the longest solves start first, which shortens the tail of the launch).
 void launch_col_solve(const Geom& g, bool masked, const double* UtU, const double* XtXall, const double* Xty, double* V, const CdParams& p,
                       unsigned long long* sweeps, unsigned long long* steps, unsigned int* queue, const unsigned char* perm_table, int* err_flag,
-                      int sm_count, int* sweeps_per_gene, const int* order, cudaStream_t st);
+                      int sm_count, int* sweeps_per_gene, const int* order, bool long_solves, cudaStream_t st);
 // dense path, alpha != 0: thread-per-gene elastic-net CD with the shared Gram UtU (k_cd_dense.cu). `order` (optional) maps
 // thread slots to genes; `sweeps_per_gene` (optional) receives every gene's sweep count.
 // `table`: cd_dense_table_elems() doubles filled by launch_cd_dense_table() from UtU (independent of Xty: may run beside

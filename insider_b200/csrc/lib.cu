@@ -487,6 +487,9 @@ struct SideSection {
     void join() { if (side != s->ctx->stream) { cudaEventRecord(s->ev_join[idx], side); cudaStreamWaitEvent(s->ctx->stream, s->ev_join[idx], 0); } }
 };
 
+// ALS iterations whose masked elastic-net solves still take hundreds of sweeps per gene (k_cd.cu: 4 lanes per gene until then)
+constexpr uint32_t CD_LONG_SOLVE_ITERS = 8;
+
 bool run_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;
     insider_resident* r = s->r;
@@ -612,7 +615,7 @@ void run_column_update(insider_session* s) {
         if (group_cd) { Launch l(s, "k_cd_order"); launch_cd_order(s->sweeps_gene, g.P, s->cd_order, s->cd_order_work, &s->state->als_iter, st); }
         Launch l(s, "k_col_solve");
         launch_col_solve(g, s->masked, s->UtU, s->XtXall, s->Xty, s->V, p, s->sweeps_dev, s->sweeps_dev + 1, s->queue, s->ctx->perm_table, s->err_dev, s->ctx->sm_count,
-                         group_cd ? s->sweeps_gene : nullptr, group_cd ? s->cd_order : nullptr, st);
+                         group_cd ? s->sweeps_gene : nullptr, group_cd ? s->cd_order : nullptr, s->iter < CD_LONG_SOLVE_ITERS, st);
     }
 }
 

@@ -9,6 +9,12 @@
 // All three stream tiles of TG = 16 genes x R rows through shared memory with cp.async.bulk (TMA 1-D bulk copies)
 // completing on mbarriers, NSTAGE deep, and contract them with mma.sync m8n8k4 f64 (DMMA). Pitches are chosen
 // (pitch % 8 == 4) so every fragment load is bank-conflict free. Accumulation order is fixed => bitwise reproducible.
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -24,6 +30,12 @@ constexpr int SLAB_ROWS_BIG = 384;      // k_row_b multi-slab
 constexpr int SLAB_ROWS_SMALL = 128;    // k_col_xty / k_sse multi-slab
 constexpr int SINGLE_SLAB_MAX_N = 384;     // 48 m-tiles of 8 rows
 
+// one TMA tensor copy: the box at (c0 = element along the contiguous dimension, c1 = row of the outer dimension) of a 2-D tensor map
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 struct StreamArgs {
@@ -413,122 +425,132 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     }
 }
 
-// k_col_xty_slabs: the multi-slab form (N > 384 rows: a tile's accumulators live across its slabs). Items = (tile, slab) of the
-// block's tile range in order, all 8 warps on the same item; reduction over rows is split over warps.
-template <int NT, bool MASKED, bool RESIDENT_U>
-__global__ void __launch_bounds__(THREADS, 1) k_col_xty_slabs(StreamArgs a) {
+// k_col_xty_slabs: the multi-slab form (N > 384 rows: U^T does not fit in shared memory and a tile's accumulators live across its
+// row slabs). Items = (group of XW_GT gene tiles, slab) of the block's tile range, all 8 warps on the same item; the reduction over
+// the slab's rows is split over warps. The slab of U^T travels with every item, so the group is XW_GT = 4 tiles wide: 64 KB of Y
+// per 32 KB of U^T, and every A fragment of U^T is reused for 4 x 2 B fragments. An item arrives by TWO tensor-map TMA copies
+// (boxes of pitchS rows x 64 genes of Y and pitchS rows x KP rows of U^T; the box is 4 rows wider than the slab so that the
+// dense box IS the bank-conflict-free pitch): measured on the GTEx-scale shard, a bulk copy costs the SM ~100 cycles whatever
+// its size, and round 1's 48 copies of 1 KB per 16-gene item ran at 0.15 of the HBM roofline (profiles/r02_gtex_shard_streaming.txt).
+constexpr int XW_GT = 4;
+
+template <int NT, bool MASKED>
+__global__ void __launch_bounds__(THREADS, 1) k_col_xty_slabs(StreamArgs a, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmU) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     int t0, t1;
     split_range(a.n_tiles, a.n_splits, blockIdx.x, t0, t1);
-    const int n_items = (t1 - t0) * a.n_slabs;
+    const int n_groups = (t1 - t0 + XW_GT - 1) / XW_GT;
+    const int n_items = n_groups * a.n_slabs;
     const int S = a.n_stages;
 
-    const int ysz = TG * a.pitchS;
+    const int ysz = XW_GT * TG * a.pitchS;
     const int usz = a.KP * a.pitchU;
-    const int stage_doubles = ysz + (RESIDENT_U ? 0 : usz);
-    double* Ures = reinterpret_cast<double*>(smem_raw);                       // resident Ut (if any)
-    double* stage0 = Ures + (RESIDENT_U ? usz : 0);
+    const int stage_doubles = ysz + usz;
+    double* stage0 = reinterpret_cast<double*>(smem_raw);
     double* scratch_own = stage0 + (size_t)S * stage_doubles;                // [NWARPS][NT*2*64] when scratch_sep
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers + 1 for Ut
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_own + (a.scratch_sep ? NWARPS * NT * 2 * 64 : 0));   // S stage barriers
 
     if (tid == 0) {
-        for (int s = 0; s <= S; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
+    // (a partial last group still loads the full box: genes of the next block's range or zero fill beyond P_pad, never used)
     auto issue = [&](int item) {
         const int s = item % S;
         double* Ys = stage0 + (size_t)s * stage_doubles;
-        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
-        const int r0 = slab * a.R;
-        const int rows_here = min(a.R, a.ldY - r0);
-        const int64_t gene = (int64_t)tile * TG;
-        const uint32_t ybytes = (uint32_t)rows_here * 8u;
-        uint32_t total = ybytes * TG;
-        if (!RESIDENT_U) total += (uint32_t)a.KP * ybytes;
-        mbar_expect_tx(&bars[s], total);
-        if (a.pitchS == a.ldY && rows_here == a.ldY) {
-            tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
-        } else {
-            for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
-        }
-        if (!RESIDENT_U) {
-            double* Us = Ys + ysz;
-            for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, ybytes, &bars[s]);
-        }
+        const int grp = item / a.n_slabs, slab = item % a.n_slabs;
+        mbar_expect_tx(&bars[s], (uint32_t)stage_doubles * 8u);
+        tma_load_2d(Ys, &tmY, slab * a.R, (t0 + grp * XW_GT) * TG, &bars[s]);
+        tma_load_2d(Ys + ysz, &tmU, slab * a.R, 0, &bars[s]);
     };
-    if (tid == 0) {
-        if (RESIDENT_U) {
-            mbar_expect_tx(&bars[S], (uint32_t)usz * 8u);
-            tma_load_1d(Ures, a.Ut, (uint32_t)usz * 8u, &bars[S]);
-        }
+    if (tid == 0)
         for (int i = 0; i < S - 1 && i < n_items; ++i) issue(i);
-    }
-    if (RESIDENT_U) mbar_wait(&bars[S], 0);
 
-    double acc[NT][2][2];
+    double acc[XW_GT][NT][2][2];
 #pragma unroll
-    for (int n = 0; n < NT; ++n)
+    for (int j = 0; j < XW_GT; ++j)
 #pragma unroll
-        for (int m = 0; m < 2; ++m) acc[n][m][0] = acc[n][m][1] = 0.0;
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) acc[j][n][m][0] = acc[j][n][m][1] = 0.0;
 
     for (int item = 0; item < n_items; ++item) {
         const int s = item % S;
         double* Ys = stage0 + (size_t)s * stage_doubles;
-        const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
-        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const double* Us = Ys + ysz;
+        const int grp = item / a.n_slabs, slab = item % a.n_slabs;
+        const int tile0 = t0 + grp * XW_GT;
+        const int nt = min(XW_GT, t1 - tile0);
         const int r0 = slab * a.R;
         const int rows_here = min(a.R, a.ldY - r0);
         if (tid == 0 && item + S - 1 < n_items) { fence_proxy_async(); issue(item + S - 1); }
-        uint32_t word = 0;
+        uint32_t word[XW_GT];
         if (MASKED) {
             const int c = tid >> 4, w = tid & 15;
-            if (32 * w < rows_here) word = __ldg(a.trC + ((int64_t)tile * TG + c) * a.Wp + (r0 >> 5) + w);
+#pragma unroll
+            for (int j = 0; j < XW_GT; ++j) {
+                word[j] = 0;
+                if (j < nt && 32 * w < rows_here) word[j] = __ldg(a.trC + ((int64_t)(tile0 + j) * TG + c) * a.Wp + (r0 >> 5) + w);
+            }
         }
         mbar_wait(&bars[s], (uint32_t)((item / S) & 1));
         if (MASKED) {
-            premask(Ys, a.pitchS, word, tid & 15, tid >> 4, rows_here);
+#pragma unroll
+            for (int j = 0; j < XW_GT; ++j)
+                if (j < nt) premask(Ys + j * TG * a.pitchS, a.pitchS, word[j], tid & 15, tid >> 4, rows_here);
             __syncthreads();
         }
         const int KS = rows_here >> 2;
         int k0, k1;
         split_range(KS, NWARPS, warp, k0, k1);
         for (int ks = k0; ks < k1; ++ks) {
-            double av[NT], bv[2];
+            double av[NT];
 #pragma unroll
             for (int n = 0; n < NT; ++n) av[n] = Us[(8 * n + g) * a.pitchU + 4 * ks + t];
 #pragma unroll
-            for (int m = 0; m < 2; ++m) bv[m] = Ys[(8 * m + g) * a.pitchS + 4 * ks + t];
+            for (int j = 0; j < XW_GT; ++j) {
+                if (j < nt) {
+                    double bv[2];
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
+                    for (int m = 0; m < 2; ++m) bv[m] = Ys[(j * TG + 8 * m + g) * a.pitchS + 4 * ks + t];
 #pragma unroll
-                for (int m = 0; m < 2; ++m) dmma(acc[n][m][0], acc[n][m][1], av[n], bv[m]);
+                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) dmma(acc[j][n][m][0], acc[j][n][m][1], av[n], bv[m]);
+                }
+            }
         }
         if (slab == a.n_slabs - 1) {
-            // cross-warp reduction in a fixed order, then store the K x 16 tile of Xty. The scratch
+            // cross-warp reduction in a fixed order, tile by tile, then store the K x 16 tile of Xty. The scratch
             // [NWARPS][NT*2*64] aliases this item's (fully consumed) stage buffer when that is large enough.
             double* scratch = a.scratch_sep ? scratch_own : Ys;
-            __syncthreads();
-            double* sc = scratch + warp * (NT * 2 * 64);
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
+            for (int j = 0; j < XW_GT; ++j) {
+                if (j < nt) {
+                    __syncthreads();
+                    double* sc = scratch + warp * (NT * 2 * 64);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[n][m][0];
-                    sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[n][m][1];
-                    acc[n][m][0] = acc[n][m][1] = 0.0;
+                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            sc[(n * 2 + m) * 64 + lane * 2 + 0] = acc[j][n][m][0];
+                            sc[(n * 2 + m) * 64 + lane * 2 + 1] = acc[j][n][m][1];
+                            acc[j][n][m][0] = acc[j][n][m][1] = 0.0;
+                        }
+                    __syncthreads();
+                    for (int x = tid; x < NT * 2 * 64; x += THREADS) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int w = 0; w < NWARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
+                        const int tl = x >> 6, ln = (x & 63) >> 1, e = x & 1;
+                        const int n = tl >> 1, m = tl & 1;
+                        const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
+                        if (k < a.ldV) a.out[((int64_t)(tile0 + j) * TG + gene) * a.ldV + k] = sum;
+                    }
                 }
-            __syncthreads();
-            for (int x = tid; x < NT * 2 * 64; x += THREADS) {
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARPS; ++w) sum += scratch[w * (NT * 2 * 64) + x];
-                const int tl = x >> 6, ln = (x & 63) >> 1, e = x & 1;
-                const int n = tl >> 1, m = tl & 1;
-                const int k = 8 * n + (ln >> 2), gene = 8 * m + 2 * (ln & 3) + e;
-                if (k < a.ldV) a.out[((int64_t)tile * TG + gene) * a.ldV + k] = sum;
             }
         }
         __syncthreads();
@@ -537,8 +559,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty_slabs(StreamArgs a) {
 
 // ------------------------------------------------------------------------------------------------------------
 // k_sse: grid (n_blocks). pred = U V per (tile, slab), residual against the Y piece, masked sums of squares.
+// Stage layout: resident U^T: [Y piece + 8 | V tile]; row slabs (N > 384): [Y box | U^T box | V tile], the two boxes by one
+// tensor-map TMA copy each (see k_col_xty_slabs: 3 copies per item instead of 49).
 template <int NT, bool MASKED, bool RESIDENT_U>
-__global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmU) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     int t0, t1;
@@ -546,10 +570,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
     const int n_items = (t1 - t0) * a.n_slabs;
     const int S = a.n_stages;
 
-    const int ysz = TG * a.pitchS + 8;
+    const int ysz = TG * a.pitchS + (RESIDENT_U ? 8 : 0);
     const int vsz = TG * a.ldV;
     const int usz = a.KP * a.pitchU;
-    const int stage_doubles = ysz + vsz + (RESIDENT_U ? 0 : usz);
+    const int stage_doubles = RESIDENT_U ? ysz + vsz : (ysz + usz + vsz + 15) / 16 * 16;      // (boxes land 128-byte aligned)
     double* Ures = reinterpret_cast<double*>(smem_raw);
     double* stage0 = Ures + (RESIDENT_U ? usz : 0);
     double* red = stage0 + (size_t)S * stage_doubles;                          // [NWARPS][4]
@@ -565,26 +589,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
     auto issue = [&](int item) {
         const int s = item % S;
         double* Ys = stage0 + (size_t)s * stage_doubles;
-        double* Vs = Ys + ysz;
         const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
         const int r0 = slab * a.R;
-        const int rows_here = min(a.R, a.ldY - r0);
-        const int rows_u = min(a.R, a.ldT - r0);
         const int64_t gene = (int64_t)tile * TG;
+        if (!RESIDENT_U) {
+            mbar_expect_tx(&bars[s], (uint32_t)(ysz + usz + vsz) * 8u);
+            tma_load_2d(Ys, &tmY, r0, (int)gene, &bars[s]);
+            tma_load_2d(Ys + ysz, &tmU, r0, 0, &bars[s]);
+            tma_load_1d(Ys + ysz + usz, a.V + gene * a.ldV, (uint32_t)vsz * 8u, &bars[s]);
+            return;
+        }
+        double* Vs = Ys + ysz;
+        const int rows_here = min(a.R, a.ldY - r0);
         const uint32_t ybytes = (uint32_t)rows_here * 8u;
-        uint32_t total = ybytes * TG + (uint32_t)vsz * 8u;
-        if (!RESIDENT_U) total += (uint32_t)a.KP * (uint32_t)rows_u * 8u;
-        mbar_expect_tx(&bars[s], total);
+        mbar_expect_tx(&bars[s], ybytes * TG + (uint32_t)vsz * 8u);
         if (a.pitchS == a.ldY && rows_here == a.ldY) {
             tma_load_1d(Ys, a.Y + gene * a.ldY, ybytes * TG, &bars[s]);
         } else {
             for (int c = 0; c < TG; ++c) tma_load_1d(Ys + c * a.pitchS, a.Y + (gene + c) * a.ldY + r0, ybytes, &bars[s]);
         }
         tma_load_1d(Vs, a.V + gene * a.ldV, (uint32_t)vsz * 8u, &bars[s]);
-        if (!RESIDENT_U) {
-            double* Us = Vs + vsz;
-            for (int k = 0; k < a.KP; ++k) tma_load_1d(Us + k * a.pitchU, a.Ut + (size_t)k * a.ldT + r0, (uint32_t)rows_u * 8u, &bars[s]);
-        }
     };
     if (tid == 0) {
         if (RESIDENT_U) {
@@ -599,8 +623,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_sse(StreamArgs a) {
     for (int item = 0; item < n_items; ++item) {
         const int s = item % S;
         const double* Ys = stage0 + (size_t)s * stage_doubles;
-        const double* Vs = Ys + ysz;
-        const double* Us = RESIDENT_U ? Ures : (Vs + vsz);
+        const double* Vs = RESIDENT_U ? Ys + ysz : Ys + ysz + usz;
+        const double* Us = RESIDENT_U ? Ures : (Ys + ysz);
         const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
         const int r0 = slab * a.R;
         const int rows_here = min(a.R, a.ldY - r0);
@@ -723,6 +747,28 @@ void launch_row_b_ex(const Geom& g, bool masked, const double* Y, const uint32_t
 }
 
 namespace {
+// 2-D tensor map over a pitched FP64 matrix [outer][pitch] (box: box_inner contiguous elements x box_outer rows), through the
+// driver entry point (the library links only the runtime)
+CUtensorMap tensor_map_2d(const double* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    alignas(64) CUtensorMap m{};
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {pitch_elems * 8};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    if (!encode || encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        throw std::runtime_error("cuTensorMapEncodeTiled failed");
+    return m;
+}
+
 // geometry shared by k_col_xty and k_sse
 bool resident_geometry(const Geom& g, StreamArgs& a, size_t extra_stage_doubles, size_t fixed_bytes) {
     const size_t ures = (size_t)g.KP * g.ldT * 8;
@@ -749,12 +795,24 @@ void launch_col_xty(const Geom& g, bool masked, const double* Y, const uint32_t*
     const bool small = (size_t)TG * g.ldY < need;                             // resident path's stage cannot hold it
     const size_t fixed = 8 * 8 + (small ? need * 8 : 0);
     const bool res = resident_geometry(g, a, 0, fixed);
-    const size_t stage = ((size_t)TG * a.pitchS + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
-    a.scratch_sep = (stage / 8 < need) ? 1 : 0;
-    const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + 8 * 8 + (a.scratch_sep ? need * 8 : 0);
-    // single slab with U^T resident: two-group kernel; row slabs (N > 384): all warps on one item, accumulators across slabs
+    size_t stage, smem;
+    alignas(64) CUtensorMap tmY{}, tmU{};
+    if (res) {
+        stage = (size_t)TG * a.pitchS * 8;
+        a.scratch_sep = (stage / 8 < need) ? 1 : 0;
+        smem = (size_t)g.KP * a.pitchU * 8 + a.n_stages * stage + 8 * 8 + (a.scratch_sep ? need * 8 : 0);
+    } else {
+        // row slabs (N > 384): XW_GT tiles + the slab of U^T per stage, double buffered
+        stage = ((size_t)XW_GT * TG * a.pitchS + (size_t)g.KP * a.pitchU) * 8;
+        a.n_stages = (int)std::min<size_t>(4, std::max<size_t>(2, (SMEM_LIMIT - 8 * 8) / stage));
+        a.scratch_sep = ((size_t)XW_GT * TG * a.pitchS < need) ? 1 : 0;
+        smem = a.n_stages * stage + 8 * 8 + (a.scratch_sep ? need * 8 : 0);
+        tmY = tensor_map_2d(Y, (uint64_t)g.ldY, (uint64_t)g.P_pad, (uint64_t)g.ldY, (uint32_t)a.pitchS, (uint32_t)(XW_GT * TG));
+        tmU = tensor_map_2d(Ut, (uint64_t)g.ldT, (uint64_t)g.KP, (uint64_t)g.ldT, (uint32_t)a.pitchU, (uint32_t)g.KP);
+    }
+    // single slab with U^T resident: two-group kernel; row slabs: all warps on one item, accumulators across slabs
 #define LAUNCH_CX(NTv, M) { set_smem(k_col_xty<NTv, M, true>, smem); k_col_xty<NTv, M, true><<<n_blocks, THREADS, smem, st>>>(a); }
-#define LAUNCH_CS(NTv, M) { set_smem(k_col_xty_slabs<NTv, M, false>, smem); k_col_xty_slabs<NTv, M, false><<<n_blocks, THREADS, smem, st>>>(a); }
+#define LAUNCH_CS(NTv, M) { set_smem(k_col_xty_slabs<NTv, M>, smem); k_col_xty_slabs<NTv, M><<<n_blocks, THREADS, smem, st>>>(a, tmY, tmU); }
 #define LAUNCH_CX2(NTv)                                                       \
     if (masked) { if (res) LAUNCH_CX(NTv, true) else LAUNCH_CS(NTv, true) } \
     else { if (res) LAUNCH_CX(NTv, false) else LAUNCH_CS(NTv, false) }
@@ -771,9 +829,16 @@ void launch_sse(const Geom& g, bool masked, const double* Y, const uint32_t* trC
     const size_t fixed = (size_t)NWARPS * 4 * 8 + 2 * TG * 16 * 4 + 8 * 8;
     const size_t extra = 8 + (size_t)TG * g.ldV;
     const bool res = resident_geometry(g, a, extra, fixed);
-    const size_t stage = ((size_t)TG * a.pitchS + extra + (res ? 0 : (size_t)g.KP * a.pitchU)) * 8;
+    size_t stage = ((size_t)TG * a.pitchS + extra) * 8;
+    alignas(64) CUtensorMap tmY{}, tmU{};
+    if (!res) {
+        stage = ((size_t)TG * a.pitchS + (size_t)g.KP * a.pitchU + (size_t)TG * g.ldV + 15) / 16 * 16 * 8;
+        a.n_stages = (int)std::min<size_t>(4, std::max<size_t>(2, (SMEM_LIMIT - fixed) / stage));
+        tmY = tensor_map_2d(Y, (uint64_t)g.ldY, (uint64_t)g.P_pad, (uint64_t)g.ldY, (uint32_t)a.pitchS, (uint32_t)TG);
+        tmU = tensor_map_2d(Ut, (uint64_t)g.ldT, (uint64_t)g.KP, (uint64_t)g.ldT, (uint32_t)a.pitchU, (uint32_t)g.KP);
+    }
     const size_t smem = (res ? (size_t)g.KP * a.pitchU * 8 : 0) + a.n_stages * stage + fixed;
-#define LAUNCH_SS(NTv, M, RS) { set_smem(k_sse<NTv, M, RS>, smem); k_sse<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a); }
+#define LAUNCH_SS(NTv, M, RS) { set_smem(k_sse<NTv, M, RS>, smem); k_sse<NTv, M, RS><<<n_blocks, THREADS, smem, st>>>(a, tmY, tmU); }
 #define LAUNCH_SS2(NTv)                                                       \
     if (masked) { if (res) LAUNCH_SS(NTv, true, true) else LAUNCH_SS(NTv, true, false) } \
     else { if (res) LAUNCH_SS(NTv, false, true) else LAUNCH_SS(NTv, false, false) }

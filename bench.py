@@ -473,6 +473,7 @@ def run_tune(args, w, rank, world, local):
                 "grid_seconds": secs, "fits": n_fits, "fits_per_second": n_fits / secs, "chosen_rank": int(best),
                 "device_loop_seconds_sum_over_fits": float((tab1[:, 2].sum() + tab2[:, 2].sum()) * 1e-3),
                 "rank_tuning": [[p[0], float(t[0]), float(t[1])] for p, t in zip(p1, tab1)],
+                "fit_device_ms": {"rank_phase_ridge": [round(float(t[2]), 1) for t in tab1], "reg_phase_elastic_net": [round(float(t[2]), 1) for t in tab2]},
                 "reg_tuning_best": [p2[int(np.argmin(tab2[:, 1]))][1], p2[int(np.argmin(tab2[:, 1]))][3], float(tab2[:, 1].min())],
                 "e2e": {"value": iters / secs, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "what": "wall clock of the whole grid between barriers: factor H2D/D2H of every fit inside, the one upload of Y/masks outside"},

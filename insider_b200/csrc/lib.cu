@@ -500,6 +500,9 @@ bool run_iteration(insider_session* s) {
         // equations] needs V only, [pass over Y -> per-level sums of B] is the long one: they run side by side (one GPU). With
         // several GPUs SB and G are adjacent and travel in ONE all-reduce, after which the factorisations follow on the chain.
         SideSection sec0(s, 0);
+        // the device-side iteration counter (permutation keys of the column update) is bumped HERE, beside the pass over Y, for the
+        // iteration that just ended: nothing before the join below reads it (6 us off the dependent chain of every iteration)
+        if (s->iter > 0) { Launch l(s, "k_bump_iter"); launch_bump_iter(s->state, sec0.side); }
         { Launch l(s, "k_gram_v"); launch_gram_v(g, s->V, s->gv_parts, s->G, s->gv_counter, nullptr, sec0.side); }
         if (s->ctx->world == 1) { Launch l(s, "k_level_factor"); launch_level_factor(g, false, s->tab_dev, s->total_levels, s->max_chunks, s->G, s->GLp, s->opt.lambda1, s->Lfac, s->err_dev, sec0.side); }
         { Launch l(s, "k_row_b"); launch_row_b_ex(g, false, r->Y, nullptr, s->V, s->SBp, nullptr, s->rb_splits, r->lv_ptr, r->lv_rows, s->total_levels, g.N * r->C, st); }
@@ -512,7 +515,7 @@ bool run_iteration(insider_session* s) {
         DenseGs dg{r->gs_lvl_first, r->gs_co_ptr, r->gs_co_row, r->gs_co_cnt, r->gs_Sx};
         { Launch l(s, "k_rows_dense_gs"); launch_rows_dense_gs_ex(g, dg, r->C, r->Q, s->total_levels, *std::max_element(r->L.begin(), r->L.end()), r->gs_nnz, s->A_all, nullptr, s->SB, s->G, s->Lfac, r->gs_row_lv, s->U, s->Ut, s->UtU, st); }
         run_column_update(s);
-        return false;
+        return true;
     }
     // sufficient statistics of the row update: G = V V' (:332), B = (M o Y) V', D_k = complement Grams
     { Launch l(s, "k_row_b"); launch_row_b(g, s->masked, r->Y, r->trC, s->V, s->Bp, s->Gp, s->rb_splits, st); }

@@ -1,5 +1,5 @@
 """Per-kernel SASS evidence of libinsider_b200.so: counts of the mnemonics that prove the sm_100a features each kernel claims
-(DMMA = FP64 tensor-core MMA, UBLKCP = cp.async.bulk / TMA 1-D bulk copy, SYNCS = mbarrier, LDS/STS, DFMA/DADD/DMUL, SHFL, BAR,
+(DMMA = FP64 tensor-core MMA, UBLKCP = cp.async.bulk / TMA 1-D bulk copy, UTMALDG = cp.async.bulk.tensor (tensor-map TMA), SYNCS = mbarrier, LDS/STS, DFMA/DADD/DMUL, SHFL, BAR,
 UCGABAR = cluster barrier) plus registers / spills from `ptxas -v`. Usage: python tools/sass_summary.py > profiles/r02_sass_summary.txt"""
 import collections
 import glob
@@ -9,7 +9,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "insider_b200", "lib", "libinsider_b200.so")
-MNEMONICS = ["DMMA", "UBLKCP", "SYNCS", "LDS", "STS", "LDGSTS", "DFMA", "DADD", "DMUL", "SHFL", "BAR", "UCGABAR", "ATOM", "RED", "LDG", "STG", "BRA"]
+MNEMONICS = ["DMMA", "UBLKCP", "UTMALDG", "SYNCS", "LDS", "STS", "LDGSTS", "DFMA", "DADD", "DMUL", "SHFL", "BAR", "UCGABAR", "ATOM", "RED", "LDG", "STG", "BRA"]
 
 
 def demangle(names):

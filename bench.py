@@ -308,6 +308,14 @@ def run_ours(args, w, rank, world, local):
 
     pc = parity_check(ctx, dist) if not args.no_parity else None
 
+    # ---- BASELINE.json config 3 beside it: the tune() grid (51 masked fits of 31 iterations) as replicas, one context per GPU
+    tg = None
+    if not args.no_tune:
+        tl = tune_leg(args, WORKLOADS["ageing_full_377x44477_K23_tune"], dist, local)
+        if rank == 0:
+            tg = {k: tl[k] for k in ("fits", "grid_seconds", "fits_per_second", "chosen_rank", "device_loop_seconds_sum_over_fits", "reg_tuning_best")}
+            tg["what"] = tl["config"]["grid"] + "; " + tl["config"]["parallelism"] + "; wall clock of the whole grid between barriers"
+
     if rank == 0:
         peaks = {}
         try:
@@ -378,6 +386,7 @@ def run_ours(args, w, rank, world, local):
             "late_phase": late,
             "time_to_global_tol": ttt,
             "parity_check": pc,
+            "tune_grid": tg,
             "cd_sweeps_per_gene_iter": out["cd_sweeps"] / max(1, Pl) / args.steps,
             "loss_after_timed": out["loss"], "wall_s_timed_region": t_wall,
         }
@@ -407,13 +416,13 @@ def tune_grid(w):
     return ranks, lams, alphas
 
 
-def run_tune(args, w, rank, world, local):
+def tune_leg(args, w, dist, local):
     """tune() grid as REPLICAS: every rank holds the full problem, the points of each phase are dealt round-robin in order of
-    decreasing expected cost; no data-path communication (the RMSE table is gathered with torch.distributed between phases)."""
+    decreasing expected cost; no data-path communication (the RMSE table is gathered with torch.distributed between phases).
+    Returns the JSON line (rank 0) or None."""
     from insider_b200 import _cabi, synth
 
-    dist = Dist(rank, world, local)
-    torch = dist.torch
+    rank, world = dist.rank, dist.world
     N, P = w["N"], w["P"]
     pb = synth.ageing_like(N=N, P=P, K=w["K"])
     tr, te = synth.random_masks(N, P, 0.1, 7)
@@ -425,7 +434,7 @@ def run_tune(args, w, rank, world, local):
     tuning_iter = args.tune_iters
 
     def run_phase(phase, points):
-        """points: (K, l1, l2, alpha); this rank runs points[rank::world]; returns the table [n, 2] of (train, test) RMSE."""
+        """points: (K, l1, l2, alpha); this rank runs points[rank::world]; returns the table [n, 4] of (train, test) RMSE, ms, iterations."""
         mine = list(range(rank, len(points), world))
         facs, optl = [], []
         for i in mine:
@@ -461,13 +470,14 @@ def run_tune(args, w, rank, world, local):
     dist.barrier()
     secs = dist.reduce(time.perf_counter() - t0)
     sampler.stop_flag = True
+    line = None
     if rank == 0:
         n_fits = len(p1) + len(p2)
         iters = float(tab1[:, 3].sum() + tab2[:, 3].sum())
         line = {"metric": "als_iterations_per_second", "value": iters / secs, "unit": "iterations/s", "n_gpus": world, "steps": int(iters),
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / iters, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "N": N, "P": P, "grid": "K 10..30 step 2 @ (0.1,0.1,0), then lambda 1..19 step 2 x alpha {.2,.3,.4,.5}",
+                "config": {"workload": "ageing_full_377x44477_K23_tune", "N": N, "P": P, "grid": "K 10..30 step 2 @ (0.1,0.1,0), then lambda 1..19 step 2 x alpha {.2,.3,.4,.5}",
                            "tuning": 1, "tuning_iter": tuning_iter, "parallelism": f"replicas: grid points round-robin over ranks, {n_rep} context(s) per GPU",
                            "l2": "no flush: Y (134 MB) exceeds L2"},
                 "grid_seconds": secs, "fits": n_fits, "fits_per_second": n_fits / secs, "chosen_rank": int(best),
@@ -478,12 +488,19 @@ def run_tune(args, w, rank, world, local):
                 "e2e": {"value": iters / secs, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "what": "wall clock of the whole grid between barriers: factor H2D/D2H of every fit inside, the one upload of Y/masks outside"},
                 "gpu_launches": None, "clocks": sampler.summary()}
-        print(json.dumps(line), flush=True)
     for r in residents[1:]:
         r.release()
     res0.release()
     for c in ctxs:
         c.close()
+    return line
+
+
+def run_tune(args, w, rank, world, local):
+    dist = Dist(rank, world, local)
+    line = tune_leg(args, w, dist, local)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     dist.close()
 
 
@@ -498,6 +515,7 @@ def main():
     ap.add_argument("--no-late", action="store_true", help="skip the steady-state (late iterations) measurement")
     ap.add_argument("--no-ttt", action="store_true", help="skip the time-to-global_tol legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg")
+    ap.add_argument("--no-tune", action="store_true", help="skip the tune() grid leg (BASELINE.json config 3 as replicas)")
     ap.add_argument("--late-start", type=int, default=150)
     ap.add_argument("--ref-genes", type=int, default=0, help="--impl reference: time only the first G genes (default: all)")
     ap.add_argument("--replicas-per-gpu", type=int, default=1, help="tune workload: concurrent contexts per GPU")

@@ -141,6 +141,21 @@ def test_multi_slab_rows_several_gene_tiles_per_block(ctx):
         assert_parity(res, fac, ro, tuning)
 
 
+def test_multi_slab_rows_wide_items_K30(ctx):
+    """The tensor-map form of the multi-slab passes (k_col_xty_slabs: 4 gene tiles per item, box copies of Y and U^T; k_sse: box
+    copies) at the GTEx configuration's rank: K = 30 (4 coordinate tiles), 5 row slabs, 5 gene tiles per block = one full group of 4 and
+    a partial one per block, the last group of the last block reaching past P_pad. Ridge column update (alpha = 0), so the oracle stays
+    cheap at this size; both tunings (masked entries zeroed in the landed box)."""
+    N, P, K = 600, 11850, 30
+    pb = synth.ageing_like(N=N, P=P, K=K, n_donors=31, seed=N)
+    tr, te = synth.random_masks(N, P, 0.1, 1)
+    F0, V0 = synth.init_factors(pb.levels, K, P, seed=2)
+    for tuning in (0, 1):
+        ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 4.0, 4.0, 0.0, tuning, 1e-12, 1e-5, 2, perm_mode=1, seed=8)
+        res, fac = gpu_optimize(ctx, pb, tr, te, F0, V0, K, 4.0, 0.0, tuning, 2, 8)
+        assert_parity(res, fac, ro, tuning)
+
+
 def test_mask_dtypes_and_heavy_masking(ctx):
     """int32 (R integer), uint8 and double masks give identical results; rows/genes that are almost fully masked."""
     N, P, K = 64, 96, 7

@@ -194,7 +194,11 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
     constexpr int LPG = GG::LPG, GPW = GG::GPW, LOG = GG::LOG, GPL = GG::GPL, NWARP = GG::WARPS, OW = GG::OW;
     constexpr int SL = KP / LPG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int MAT = KP * SL * 16;                                          // doubles per GPL interleaved matrices
+    // (Measured and dropped, profiles/r02_masked_solver_versions.txt v14: keeping only the lower triangle of every matrix - 2.4 instead of
+    // 4.6 KB per gene, 9 instead of 5 one-warp blocks per SM, both access directions bank-conflict free with element t = r(r+1)/2 + c of
+    // gene slot h at 4t + h - costs a compare, two selects and an add per load: 92 instead of 62 instructions per step, iteration 0
+    // 101 instead of 83 ms.)
+    constexpr int MAT = KP * SL * 16;                                          // doubles per set of GPL interleaved matrices
     auto XI = [](int r, int c) -> int { return (r * SL + (c >> LOG)) * 16 + (c & (LPG - 1)); };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> LOG, li = lane & (LPG - 1);
     const int grp_shift = grp << LOG;
@@ -206,6 +210,16 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
     unsigned char* ord_all = reinterpret_cast<unsigned char*>(sh_all + (size_t)NWARP * GPW * 3 * KP);
     const int gslot = warp * GPW + grp;
     double* Xs = PERGENE ? Xall_s + (size_t)(gslot / GPL) * MAT + (gslot % GPL) * LPG : Xall_s;
+    // row k, this lane's slot s: one shared-memory byte address = lane constant + k * row pitch
+    const uint32_t xs_base = smem_u32(Xs);
+    uint32_t cA[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) cA[s] = xs_base + (uint32_t)(s * 16 + li) * 8u;
+    // (measured, masked iteration 0: the explicit-address form wins with 8 lanes per gene, 91.8 -> 87.3 ms, and loses with 4, 83.1 -> 91.9 ms)
+    auto XR = [&](int k, int s) -> double {
+        if (LPG == 8) return lds64(cA[s] + (uint32_t)k * (uint32_t)(SL * 16 * 8));
+        return Xs[(k * SL + s) * 16 + li];
+    };
     double* sh = sh_all + (size_t)gslot * 3 * KP;
     unsigned char* ord_s = ord_all + gslot * 32;
     double* Bc = sh; double* DRc = sh + KP;            // beta [KP] | ((XtX_kk + l2)/2, 1/(XtX_kk + l2)) pairs [2*KP]   (16-byte aligned: KP % 8 == 0)
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
                         const double bm = __shfl_sync(gmask, beta[ms], ml, LPG);
                         if (m < K && bm != 0.0) {
 #pragma unroll
-                            for (int s = 0; s < SL; ++s) q[s] = fma(-Xs[(m * SL + s) * 16 + li], bm, q[s]);
+                            for (int s = 0; s < SL; ++s) q[s] = fma(-XR(m, s), bm, q[s]);
                         }
                     }
                 __syncwarp(gmask);
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
             int k = ob(0), kn = (1 < K) ? ob(1) : ob(0);                                      // (K == KP - 7 == 1 is possible)
             double xr[SL];
 #pragma unroll
-            for (int s = 0; s < SL; ++s) xr[s] = Xs[(k * SL + s) * 16 + li];
+            for (int s = 0; s < SL; ++s) xr[s] = XR(k, s);
             double2 dr = *reinterpret_cast<const double2*>(DRc + 2 * k);                  // (XtX_kk + l2) / 2, 1 / (XtX_kk + l2)
             double bo = Bc[k], xkn = Xs[XI(k, kn)];
             double up = __shfl_sync(FULL, sel_slot(k), k & (LPG - 1), LPG);               // :94 - the state is the upper itself (p form)
@@ -365,7 +379,7 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
                 // operands of step i + 1 (addresses depend on the order only) and its upper as of BEFORE this step's update
                 double xrn[SL];
 #pragma unroll
-                for (int s = 0; s < SL; ++s) xrn[s] = Xs[(kn * SL + s) * 16 + li];
+                for (int s = 0; s < SL; ++s) xrn[s] = XR(kn, s);
                 const double2 drn = *reinterpret_cast<const double2*>(DRc + 2 * kn);
                 const double xknn = Xs[XI(kn, knn)];
                 const double shn = __shfl_sync(FULL, sel_slot(kn), kn & (LPG - 1), LPG);

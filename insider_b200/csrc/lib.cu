@@ -92,6 +92,10 @@ struct insider_ctx {
     ncclComm_t comm = nullptr;
     bool profile = false;
     unsigned char* perm_table = nullptr;    // rank tables of the counter-based permutation source (common.cuh)
+    // pinned bounce buffers for uploads from PAGEABLE host memory (what R passes): see h2d_staged()
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    bool pin_busy[2] = {false, false};
 };
 
 struct insider_resident {
@@ -225,6 +229,39 @@ void split_genes(int64_t P, int world, int rank, int64_t& j0, int64_t& n) {
 }
 
 // ---- upload -------------------------------------------------------------------------------------------------
+// Host-to-device copy that does not depend on where the caller's buffer lives. From pinned memory: one cudaMemcpyAsync. From
+// pageable memory (R's matrices) the driver stages every copy through its own small pinned buffer at 9-13 GB/s; here the source is
+// copied by 4 host threads into two 16 MB pinned bounce buffers whose DMA transfers overlap the next chunk's memcpy
+// (142 MB of Y: 15.7 -> ~7 ms, bench.py `e2e_pageable`).
+constexpr size_t PIN_BYTES = (size_t)16 << 20;
+void h2d_staged(insider_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    cudaPointerAttributes at{};
+    const bool pageable = bytes >= ((size_t)4 << 20) && cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (!pageable) { CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return; }
+    for (int b = 0; b < 2; ++b) {
+        if (!ctx->pin[b]) { CUDA_TRY(cudaHostAlloc(&ctx->pin[b], PIN_BYTES, cudaHostAllocDefault)); CUDA_TRY(cudaEventCreateWithFlags(&ctx->pin_ev[b], cudaEventDisableTiming)); }
+    }
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += PIN_BYTES, b ^= 1) {
+        const size_t n = std::min(PIN_BYTES, bytes - off);
+        if (ctx->pin_busy[b]) { CUDA_TRY(cudaEventSynchronize(ctx->pin_ev[b])); ctx->pin_busy[b] = false; }   // its last DMA has read the buffer
+        constexpr int T = 4;
+        std::thread th[T - 1];
+        const size_t part = (n / T + 63) & ~(size_t)63;
+        auto piece = [&](int t) {
+            const size_t o = std::min(n, (size_t)t * part), e = std::min(n, o + part);
+            if (e > o) memcpy((char*)ctx->pin[b] + o, (const char*)src + off + o, e - o);
+        };
+        for (int t = 1; t < T; ++t) th[t - 1] = std::thread(piece, t);
+        piece(0);
+        for (int t = 1; t < T; ++t) th[t - 1].join();
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + off, ctx->pin[b], n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ctx->pin_ev[b], st));
+        ctx->pin_busy[b] = true;
+    }
+}
+
 insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
     REQUIRE(pb && pb->Y && pb->N > 0 && pb->P > 0, "problem: Y, N, P required");
     REQUIRE(pb->C >= 0 && (pb->C == 0 || pb->levels), "problem: levels required when C > 0");
@@ -259,8 +296,8 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
             CUDA_TRY(cudaMallocAsync((void**)&stage, (size_t)chunk * N * 8, st));
             for (int64_t c0 = 0; c0 < r->Pl; c0 += chunk) {
                 const int64_t n = std::min(chunk, r->Pl - c0);
-                cudaError_t e = cudaMemcpyAsync(stage, pb->Y + (size_t)(r->j0 + c0) * N, (size_t)n * N * 8, cudaMemcpyHostToDevice, st);
-                if (e != cudaSuccess) { cudaFreeAsync(stage, st); CUDA_TRY(e); }
+                try { h2d_staged(ctx, stage, pb->Y + (size_t)(r->j0 + c0) * N, (size_t)n * N * 8, st); }
+                catch (...) { cudaFreeAsync(stage, st); throw; }
                 launch_repitch(r->Y + (size_t)c0 * r->ldY, r->ldY, stage, N, N, n, st);
             }
             cudaFreeAsync(stage, st);
@@ -359,7 +396,7 @@ insider_resident* do_upload(insider_ctx* ctx, const insider_problem* pb) {
                     uint32_t* dst = pass == 0 ? r->trC : r->teC;
                     for (int64_t c0 = 0; c0 < r->Pl; c0 += chunk) {
                         const int64_t n = std::min(chunk, r->Pl - c0);
-                        CUDA_TRY(cudaMemcpyAsync(tmp, src + (size_t)(r->j0 + c0) * N * esz, (size_t)n * N * esz, cudaMemcpyHostToDevice, st));
+                        h2d_staged(ctx, tmp, src + (size_t)(r->j0 + c0) * N * esz, (size_t)n * N * esz, st);
                         launch_pack_mask(tmp, pb->mask_kind, N, n, r->Wp, dst + (size_t)c0 * r->Wp, st);
                         r->h2d_bytes += (double)n * N * esz;
                     }
@@ -924,6 +961,7 @@ void insider_b200_ctx_destroy(insider_ctx* c) {
     cudaSetDevice(c->device);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     if (c->perm_table) cudaFree(c->perm_table);
+    for (int b = 0; b < 2; ++b) { if (c->pin_ev[b]) cudaEventDestroy(c->pin_ev[b]); if (c->pin[b]) cudaFreeHost(c->pin[b]); }
     if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
     auto issue = [&](int item) {
         const int s = item % S;
         double* Ys = stage0 + (size_t)s * stage_doubles;
-        const int tile = t0 + item / a.n_slabs, slab = item % a.n_slabs;
+        const int tile = t1 - 1 - item / a.n_slabs, slab = item % a.n_slabs;      // (backwards: see below)
         const int r0 = slab * a.R;
         const int rows_here = min(a.R, a.ldY - r0);
         const int64_t gene = (int64_t)tile * TG;
@@ -356,7 +356,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_col_xty(StreamArgs a) {
         for (int m = 0; m < 2; ++m) acc[n][m][0] = acc[n][m][1] = 0.0;
 
     for (int tl = grp; tl < n_tiles_blk; tl += 2) {
-        const int tile = t0 + tl;
+        // The block walks its tile range BACKWARDS: k_row_b, the other pass over Y of an iteration, walks the same range forwards, so each
+        // pass starts on the tiles the previous one touched last - the part of the 134 MB matrix that is still in the 126 MB L2
+        // (measured: k_row_b 45.7 -> 44.0 us, k_col_xty 40.4 -> 39.5 us; two blocks per SM for k_row_b: 46.1 us, dropped).
+        const int tile = t1 - 1 - tl;
         for (int slab = 0; slab < a.n_slabs; ++slab) {
             const int item = tl * a.n_slabs + slab;
             const int s = item % S;

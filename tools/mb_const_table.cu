@@ -2,6 +2,10 @@
 //   smem : 12 broadcast LDS.128 per step (what k_cd_dense does), row index dynamic
 //   const: `switch (k)` to 24 step bodies whose 24 FMA operands are compile-time addresses in a __constant__ table
 //          (no LDS at all; the question is whether the constant cache sustains a 4.6 KB table visited in random order)
+//   dmma : the rank-1 update q -= delta x row on the FP64 tensor pipe WITHOUT leaving the thread-per-gene layout: tile j of 12 holds
+//          coordinates 2j, 2j+1 of all 32 genes as an m8n8k4 accumulator (thread (r, c) = gene 4r + c), A = the thread's own delta,
+//          B = block-diagonal [c'' == c'] x row[2j + e] (one non-broadcast LDS.64 per tile and lane): 12 DMMAs per step, each doing
+//          64 useful of its 256 FMAs
 // One warp per block like k_cd_dense; reports cycles per warp-step for a lone warp and for 8 blocks per SM.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/mb_const_table tools/mb_const_table.cu
 #include <cstdio>
@@ -81,6 +85,43 @@ __global__ void __launch_bounds__(32, 8) k_smem(const double* tab_g, double* out
     out[blockIdx.x * 32 + threadIdx.x] = s;
 }
 
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(32, 8) k_dmma(const double* tab_g, double* out, int steps, double la) {
+    __shared__ __align__(16) double tab[KT * KT];
+    __shared__ unsigned char ord[4096];
+    for (int x = threadIdx.x; x < KT * KT; x += 32) tab[x] = tab_g[x];
+    for (int x = threadIdx.x; x < 4096; x += 32) ord[x] = cord[x];
+    __syncwarp();
+    const int lane = threadIdx.x, kk = lane & 3, nn = lane >> 2;       // B fragment element (k = lane % 4, n = lane / 4)
+    const bool nz = kk == (nn >> 1);                                   // block diagonal: column n belongs to c' = n / 2
+    const int e = nn & 1;
+    double q[KT];                                                      // q[2j], q[2j+1]: accumulator pair of tile j
+#pragma unroll
+    for (int l = 0; l < KT; ++l) q[l] = 1.0 + 0.01 * l + 1e-3 * threadIdx.x;
+    for (int i = 0; i < steps; ++i) {
+        const int k = ord[(i + blockIdx.x * 7) & 4095];
+        const double* row = tab + k * KT;
+        // scalar chain on this thread's gene (coordinate k is dynamic here: the microbenchmark reads a fixed register, the real kernel
+        // would relabel as k_cd_dense does)
+        const double up = q[0];
+        const double t1 = fabs(up) - la;
+        double nb = copysign(t1, up) * row[k];
+        nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
+        const double nd = -nb * 1e-3;
+#pragma unroll
+        for (int j = 0; j < KT / 2; ++j) {
+            const double b = nz ? row[2 * j + e] : 0.0;
+            dmma884(q[2 * j], q[2 * j + 1], nd, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int l = 0; l < KT; ++l) s += q[l];
+    out[blockIdx.x * 32 + threadIdx.x] = s;
+}
+
 int main() {
     double h[KT * KT];
     srand(1);
@@ -96,18 +137,19 @@ int main() {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int steps = 24 * 20000;
     for (int blocks : {1, 148, 148 * 4, 148 * 8}) {
-        for (int v = 0; v < 2; ++v) {
+        for (int v = 0; v < 3; ++v) {
             float best = 1e9;
             for (int rep = 0; rep < 3; ++rep) {
                 CK(cudaEventRecord(e0));
-                if (v == 0) k_smem<<<blocks, 32>>>(tab_g, out, steps, 0.5); else k_const<<<blocks, 32>>>(out, steps, 0.5);
+                if (v == 0) k_smem<<<blocks, 32>>>(tab_g, out, steps, 0.5); else if (v == 1) k_const<<<blocks, 32>>>(out, steps, 0.5);
+                else k_dmma<<<blocks, 32>>>(tab_g, out, steps, 0.5);
                 CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
             }
             CK(cudaGetLastError());
             const double clk = best * 1e-3 * khz * 1e3;
             const double per_sm = (blocks + 147) / 148;
-            printf("%s blocks %5d: %.3f ms, %.1f clk per warp-step (one warp), %.1f clk per warp-step per SM\n", v ? "const" : "smem ", blocks, best,
+            printf("%s blocks %5d: %.3f ms, %.1f clk per warp-step (one warp), %.1f clk per warp-step per SM\n", v == 0 ? "smem " : v == 1 ? "const" : "dmma ", blocks, best,
                    clk / steps, clk / steps / per_sm);
         }
     }

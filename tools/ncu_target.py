@@ -1,4 +1,4 @@
-"""Short target for ncu: a few ALS iterations at the bench shape. Usage: python tools/ncu_target.py [tuning] [iters] [P]"""
+"""Short target for ncu: a few ALS iterations at the bench shape. Usage: python tools/ncu_target.py [tuning] [iters] [P] [N] [K]"""
 import sys
 sys.path.insert(0, ".")
 from insider_b200 import _cabi, synth
@@ -6,7 +6,8 @@ from insider_b200 import _cabi, synth
 tuning = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 P = int(sys.argv[3]) if len(sys.argv) > 3 else 44477
-N, K = 377, 23
+N = int(sys.argv[4]) if len(sys.argv) > 4 else 377
+K = int(sys.argv[5]) if len(sys.argv) > 5 else 23
 pb = synth.ageing_like(N=N, P=P, K=K)
 tr, te = synth.random_masks(N, P, 0.1, 7)
 F0, V0 = synth.init_factors(pb.levels, K, P, seed=1)

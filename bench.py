@@ -523,7 +523,7 @@ def main():
     ap.add_argument("--no-tune", action="store_true", help="skip the tune() grid leg (BASELINE.json config 3 as replicas)")
     ap.add_argument("--late-start", type=int, default=150)
     ap.add_argument("--ref-genes", type=int, default=0, help="--impl reference: time only the first G genes (default: all)")
-    ap.add_argument("--replicas-per-gpu", type=int, default=1, help="tune workload: concurrent contexts per GPU")
+    ap.add_argument("--replicas-per-gpu", type=int, default=2, help="tune workload: concurrent contexts per GPU (2: one fit's tail overlaps the other's bulk, measured 12.3 -> 11.2 s on one GPU)")
     ap.add_argument("--tune-iters", type=int, default=30, help="tune workload: tuning_iter")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

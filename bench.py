@@ -88,6 +88,10 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.005)
 
+    def mark(self):
+        """Start of the timed region: forget what was sampled before (the thread is started early so that NVML's slow first calls are over)."""
+        self.samples, self.reasons = [], set()
+
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
@@ -239,17 +243,18 @@ def run_ours(args, w, rank, world, local):
     res = ctx.upload(prob)
 
     # ---- warm-up: same kernels, same data, throw-away session
+    sampler = ClockSampler(local)
+    sampler.start()
     if args.warmup > 0:
         s = res.begin(_cabi.HostFactors(F0, V0, K), opts(10 ** 6))
         s.step(args.warmup)
         s.end(read_factors=False)
 
     # ---- timed region: iterations 0..K-1, device-timed inside the library (CUDA events on its stream)
-    sampler = ClockSampler(local)
     fac = _cabi.HostFactors(F0, V0, K)
     s = res.begin(fac, opts(10 ** 6))
     dist.barrier()
-    sampler.start()
+    sampler.mark()
     t_wall = time.perf_counter()
     done, ms = s.step(args.steps)
     torch.cuda.synchronize()

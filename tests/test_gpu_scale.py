@@ -229,3 +229,29 @@ def test_visiting_order_deviation_reference_stream_vs_counter_based(ctx):
         assert abs(cg["loss"] - ca["loss"]) <= ORDER_TOL_LOSS * ca["loss"]
         assert abs(cg["test_rmse"] - ca["test_rmse"]) <= ORDER_TOL_TEST_RMSE * ca["test_rmse"]
         assert abs(cg["train_rmse"] - ca["train_rmse"]) <= ORDER_TOL_TRAIN_RMSE * ca["train_rmse"]
+
+
+def test_config4_row_count_17382_two_confounders(ctx):
+    """BASELINE.json config 4's row geometry at full size - N = 17 382 samples, tissue (54 levels) x donor (948 levels), K = 30: 46
+    row slabs of 384 in k_row_b, 136 slabs of 128 in the tensor-map k_col_xty_slabs / k_sse, 1002 level systems in the dense
+    Gauss-Seidel sweep - on a slice of genes small enough for the oracle (its residual-form elastic net costs 17 382 flops per
+    coordinate step: the elastic-net cases stop their inner solves at sub_tol = 1, ~140 sweeps per gene instead of thousands).
+    Ridge fits, masked and dense, on 160 genes; elastic-net fits, masked and dense, on 32."""
+    N, K = 17382, 30
+    for P, tuning, alpha, stol in ((160, 0, 0.0, 1e-5), (160, 1, 0.0, 1e-5), (32, 0, 0.4, 1.0), (32, 1, 0.4, 1.0)):
+        pb = synth.gtex_like(N=N, P=P, K=K)
+        tr, te = synth.random_masks(N, P, 0.1, 1)
+        F0, V0 = synth.init_factors(pb.levels, K, P, seed=2)
+        ro = oracle.optimize(pb.Y, F0, V0, pb.confounder, None, tr, te, 0, K, 4.0, 4.0, alpha, tuning, 1e-12, stol, 1, perm_mode=1, seed=8)
+        prob = _cabi.HostProblem(pb.Y, pb.confounder, None, tr, te, 0)
+        fac = _cabi.HostFactors(F0, V0, K)
+        opt = _cabi.default_options()
+        opt.lambda1 = opt.lambda2 = 4.0
+        opt.alpha, opt.tuning, opt.global_tol, opt.sub_tol, opt.max_iter, opt.seed = alpha, tuning, 1e-12, stol, 1, 8
+        rg = ctx.optimize(prob, fac, opt)
+        assert rg["iters_run"] == ro.iters_run
+        assert rel(fac.V, ro.column_factor) <= 1e-8
+        for a, b in zip(fac.factors, ro.factors):
+            assert rel(a, b) <= 1e-8
+        assert abs(rg["loss"] - ro.loss) <= 1e-10 * abs(ro.loss)
+        assert rg["cd_sweeps"] == ro.cd_sweeps

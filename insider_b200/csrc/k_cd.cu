@@ -15,14 +15,13 @@
 // State form: p_k = q_k + beta_k XtX_kk (the "upper" of coordinate_descent.cpp:94) is what the lanes hold - see k_cd_dense.cu.
 // Visit order: counter-based permutation identical to the oracle's mode B.
 //
-// Mapping (k_cd_persistent): 8 lanes per gene, 4 genes per warp, lane li of a group holds q of coordinates li, li+8, li+16,
-// (li+24) in registers for the whole solve (coordinate layout; no per-sweep relayout). Groups pull genes from an atomic queue
-// (sweep counts vary 4x between genes) and run independently: each has its own sweep index and therefore its own visiting
-// order. A step for coordinate k: select the slot k>>3 (group-uniform), broadcast q_k from lane k&7 with one 64-bit shuffle,
-// every lane computes the same scalar update from the group's shared beta / diagonal arrays, then updates its own q with its
-// 3-4 elements of row k of the gene's Gram matrix (8 consecutive doubles per group: conflict-free). ~12 shared-memory
-// wavefronts per 4 gene-steps; the previous version (position layout re-built through shared memory every sweep, gathers of
-// permuted columns) spent 31 (profiles/r01_ncu_k_cd_persistent_v5_dense_A.txt).
+// Mapping (k_cd_persistent): LPG lanes per gene (8, or 4 in the long solves of the first ALS iterations), 32 / LPG genes per warp;
+// lane li of a group holds p of coordinates li, li + LPG, .. in registers for the whole solve (coordinate layout; no per-sweep
+// relayout). Groups pull genes from an atomic queue (sweep counts vary 4x between genes) and run independently: each has its own
+// sweep index and therefore its own visiting order. A step for coordinate k: every lane computes the same scalar update from the
+// group's shared beta / diagonal arrays and the upper of k - which arrived one step EARLIER (look-ahead, see the kernel) - then
+// updates its own p with its elements of row k of the gene's Gram matrix (LPG consecutive doubles per group, the groups of a warp
+// interleaved per 128-byte line: conflict-free). History of the step: profiles/r02_masked_solver_versions.txt.
 #include <algorithm>
 #include <cstdlib>
 

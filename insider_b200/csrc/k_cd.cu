@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
                 for (int s = 0; s < SL; ++s) {
                     const int c = s * LPG + li;
                     const double d = PERGENE ? Xs[XI(c, c)] : ((c < K) ? a.Xsh[(size_t)c * a.xs_r + (size_t)c * a.xs_c] : 0.0);
-                    Bc[c] = beta[s]; DRc[2 * c] = 0.5 * (d + l2); DRc[2 * c + 1] = 1.0 / (d + l2);
+                    // an EXCLUDED coordinate gets 1/den = 0: its step computes new = +-0 = old, delta = +-0, and every FMA of the step is
+                    // an exact no-op - no test of the active set inside the step (5 instructions of ~60)
+                    Bc[c] = beta[s]; DRc[2 * c] = 0.5 * (d + l2); DRc[2 * c + 1] = ((inc >> c) & 1u) ? 1.0 / (d + l2) : 0.0;
                 }
                 __syncwarp(gmask);
 #pragma unroll
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
         ++draw;
         __syncwarp();
         // ---- one sweep: step i visits coordinate k = ord[i] of every group (groups are at different sweeps: k differs per group)
-        const uint32_t incs = active ? inc : 0u;                                          // finished / retired groups: all steps are no-ops
+        // (a retired group keeps stepping on its last gene's state: a converged solve, never written back)
         double dl = 0.0;
         {
             uint32_t ow[KP / 4];
@@ -384,11 +386,9 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
                 const double shn = __shfl_sync(FULL, sel_slot(kn), kn & (LPG - 1), LPG);
                 const double bon = Bc[kn];
                 // the step itself (coordinate_descent.cpp:94-109)
-                const bool on = (incs >> k) & 1u;
                 const double t1 = fabs(up) - la;
-                double nb = copysign(t1, up) * dr.y;                                          // :99-104
+                double nb = copysign(t1, up) * dr.y;                                          // :99-104 (excluded coordinate: dr.y = 0)
                 nb = (__double2hiint(t1) >= 0) ? nb : 0.0;
-                nb = on ? nb : bo;                                                            // excluded coordinate / idle group: no-op
                 const double dlt = nb - bo;
                 const double nd = -dlt;
                 const double upn = fma(nd, xkn, shn);                                         // what the owner of k_next computes below
@@ -425,10 +425,15 @@ __global__ void __launch_bounds__(GroupGeom<LPGv>::WARPS * 32) k_cd_persistent(C
                 if (vmask == 0u || sweeps >= MAX_SWEEPS) {
                     // finished: write the gene back
 #pragma unroll
-                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = Bc[c]; }
+                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if (c < K) a.Vout[gene * a.ldv + c] = Bc[c] + 0.0; }   // (+ 0.0: an excluded coordinate may hold -0)
                     if (li == 0) { sweeps_acc += (unsigned long long)sweeps; if (a.sweeps_per_gene) a.sweeps_per_gene[gene] = sweeps; }
                     active = false;
-                } else { inc |= vmask; n_inc = __popc(inc); }
+                } else {
+                    // re-admitted coordinates get their 1/den back: 1 / (2 * ((XtX_kk + l2) / 2)), bitwise the set-up's quotient
+#pragma unroll
+                    for (int s = 0; s < SL; ++s) { const int c = s * LPG + li; if ((vmask >> c) & 1u) DRc[2 * c + 1] = 1.0 / (2.0 * DRc[2 * c]); }
+                    inc |= vmask; n_inc = __popc(inc);
+                }
             }
         }
     }

@@ -525,7 +525,7 @@ struct SideSection {
 };
 
 // ALS iterations whose masked elastic-net solves still take hundreds of sweeps per gene (k_cd.cu: 4 lanes per gene until then)
-constexpr uint32_t CD_LONG_SOLVE_ITERS = 8;
+constexpr uint32_t CD_LONG_SOLVE_ITERS = 6;
 
 bool run_iteration(insider_session* s) {
     cudaStream_t st = s->ctx->stream;

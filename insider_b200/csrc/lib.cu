@@ -253,9 +253,13 @@ void h2d_staged(insider_ctx* ctx, void* dst, const void* src, size_t bytes, cuda
             const size_t o = std::min(n, (size_t)t * part), e = std::min(n, o + part);
             if (e > o) memcpy((char*)ctx->pin[b] + o, (const char*)src + off + o, e - o);
         };
-        for (int t = 1; t < T; ++t) th[t - 1] = std::thread(piece, t);
+        bool spawned[T - 1] = {false, false, false};
+        for (int t = 1; t < T; ++t) {
+            try { th[t - 1] = std::thread(piece, t); spawned[t - 1] = true; }
+            catch (...) { piece(t); }                                          // no thread to be had: copy this piece here
+        }
         piece(0);
-        for (int t = 1; t < T; ++t) th[t - 1].join();
+        for (int t = 1; t < T; ++t) if (spawned[t - 1]) th[t - 1].join();
         CUDA_TRY(cudaMemcpyAsync((char*)dst + off, ctx->pin[b], n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(ctx->pin_ev[b], st));
         ctx->pin_busy[b] = true;

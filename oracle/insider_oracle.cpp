@@ -8,10 +8,16 @@
 // trick, per-gene elastic-net coordinate descent in RESIDUAL form with a loss-difference stopping rule,
 // evaluation every 10th iteration with the decay ladder.
 //
-// PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for this path and cannot be
-// built here (needs R + Rcpp + RcppArmadillo + BLAS/LAPACK, none present). This restatement is pinned
-// instead by (1) an independently written NumPy/SciPy twin (oracle/numpy_twin.py), (2) analytic optimality
-// checks (KKT / normal-equation residuals / monotone loss) in tests/, (3) R-RNG known answers.
+// PARITY PIN: the reference ships no golden vectors / known-answer tests for this path, and as shipped it cannot be built here
+// (it needs R + Rcpp + RcppArmadillo + BLAS/LAPACK, none present). Its ALGORITHM sources, however, compile where they lie against
+// a small Armadillo / Rcpp API shim of ours (oracle/ref_shim/, `make -C oracle ref` -> oracle/_ref/libinsider_ref.so), and
+// tests/test_ref_pin.py runs this restatement (mode A, one thread) against them: optimize() on ridge / elastic-net x masked /
+// dense fits, with continuous covariates, to convergence through the decay ladder, and at 377 x 320 with K = 23;
+// strong_coordinate_descent() and optimize_continuous_v2() directly - factors to 1e-13..1e-15, identical sweep counts. What that
+// pin does NOT cover is the arithmetic below the reference's own code: the shim's products / Cholesky stand in for BLAS / LAPACK,
+// and arma::randperm under R's RNG is restated from memory on both sides (R's runif known answers hold).
+// Further pins: (1) an independently written NumPy/SciPy twin (oracle/numpy_twin.py), (2) analytic optimality checks (KKT /
+// normal-equation residuals / monotone loss) in tests/, (3) R-RNG known answers.
 //
 // Third-party arithmetic the reference delegates to and that is restated here:
 //   * arma::solve(A, b, solve_opts::likely_sympd)  -> LAPACK dposv-style Cholesky (chol_solve below). The

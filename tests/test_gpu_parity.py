@@ -156,6 +156,34 @@ def test_multi_slab_rows_wide_items_K30(ctx):
         assert_parity(res, fac, ro, tuning)
 
 
+def test_gpu_matches_the_reference_sources_directly(ctx):
+    """No oracle in between: the CUDA path against oracle/_ref/libinsider_ref.so, the reference's own optimize.cpp / utils.cpp compiled
+    against the API shim (oracle/ref.py). Ridge column updates (alpha = 0) use no random coordinate order, so the two are comparable to
+    rounding: masked and dense fits, with and without continuous covariates, 12 iterations."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libinsider_ref.so not built")
+    cases = []
+    pb = synth.ageing_like(N=120, P=400, K=10, n_donors=17, seed=4)
+    cases.append((pb, None, 10, synth.init_factors(pb.levels, 10, 400, seed=3)))
+    pc = synth.with_continuous(N=90, P=300, K=6, levels=(3, 5), Q=2, seed=12)
+    cases.append((pc, pc.X, 6, synth.init_factors(pc.levels, 6, 300, Q=2, seed=5)))
+    for pbx, X, K, (F0, V0) in cases:
+        N, P = pbx.Y.shape
+        tr, te = synth.random_masks(N, P, 0.1, 6)
+        for tuning in (1, 0):
+            Fr, Vr, trm, tem, loss = ref.optimize(pbx.Y, F0, V0, pbx.confounder, X, tr, te, 1 if X is not None else 0, K, 3.0, 3.0, 0.0, tuning,
+                                                  1e-12, 1e-5, 11, r_seed=1)
+            res, fac = gpu_optimize(ctx, pbx, tr, te, F0, V0, K, 3.0, 0.0, tuning, 11, 9, X=X)
+            assert rel(fac.V, Vr) <= FACTOR_TOL
+            for a, b in zip(fac.factors, Fr):
+                assert rel(a, b) <= FACTOR_TOL
+            assert abs(res["loss"] - loss) <= SCALAR_TOL * abs(loss)
+            assert abs(res["train_rmse"] - trm) <= SCALAR_TOL * trm
+            if tuning == 1:
+                assert abs(res["test_rmse"] - tem) <= SCALAR_TOL * tem
+
+
 def test_mask_dtypes_and_heavy_masking(ctx):
     """int32 (R integer), uint8 and double masks give identical results; rows/genes that are almost fully masked."""
     N, P, K = 64, 96, 7

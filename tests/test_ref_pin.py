@@ -78,6 +78,21 @@ def test_optimize_with_continuous_covariates(tuning):
     compare(pb, tr, te, F0, V0, K, 2.0, 0.3, tuning, 11, X=pb.X)
 
 
+@pytest.mark.parametrize("case", range(16))
+def test_random_shapes_designs_and_penalties(case):
+    """Seeded random problems: 1-3 categorical confounders with 2-9 levels, 0-2 continuous covariates, K = 1..7, alpha in {0, 0.3, 1},
+    both tunings, masking ratios 5-40 %."""
+    rng = np.random.default_rng(1000 + case)
+    N, P, K = int(rng.integers(14, 44)), int(rng.integers(9, 40)), int(rng.integers(1, 8))
+    levels = tuple(int(v) for v in rng.integers(2, 10, size=int(rng.integers(1, 4))))
+    Q = int(rng.integers(0, 3))
+    pb = synth.with_continuous(N=N, P=P, K=K, levels=levels, Q=Q, seed=case + 50)
+    tr, te = synth.random_masks(N, P, float(rng.uniform(0.05, 0.4)), case)
+    F0, V0 = synth.init_factors(pb.levels, K, P, Q=Q, seed=case)
+    alpha = [0.0, 0.3, 1.0][case % 3]
+    compare(pb, tr, te, F0, V0, K, float(rng.uniform(0.5, 6.0)), alpha, case % 2, 11, X=pb.X if Q else None, r_seed=case + 1)
+
+
 def test_run_to_convergence_decay_ladder_and_break():
     """global_tol reached: the break iteration and the sub_tol decay ladder (src/optimize.cpp:381-407) decide the final state; equal final
     factors mean the restatement broke at the same evaluation with the same ladder."""

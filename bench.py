@@ -140,13 +140,33 @@ def run_reference(args, w, rank):
     value = args.steps / secs * (P / w["P"])
     sample = (f"all {w['P']} genes, iterations 0..{args.steps - 1} (measured, no extrapolation)" if P == w["P"] else
               f"first {P} of {w['P']} genes, iterations 0..{args.steps - 1}; EXTRAPOLATED by {P}/{w['P']}")
+    # the timed implementation is the PORT (oracle/insider_oracle.cpp); where oracle/_ref exists (the reference's own sources compiled against
+    # oracle/ref_shim/, serial) a small fit shows that the port computes what the reference's code computes
+    port_check = None
+    try:
+        from oracle import ref
+        from insider_b200 import synth
+        if ref.available():
+            pbs = synth.ageing_like(N=80, P=120, K=8, n_donors=13, seed=3)
+            trs, tes = synth.random_masks(80, 120, 0.1, 6)
+            F0s, V0s = synth.init_factors(pbs.levels, 8, 120, seed=7)
+            oracle.set_threads(1)
+            ro = oracle.optimize(pbs.Y, F0s, V0s, pbs.confounder, None, trs, tes, 0, 8, 3.0, 3.0, 0.4, 1, 1e-12, 1e-5, 11, perm_mode=0, r_seed=42)
+            Fr, Vr, _, _, lr = ref.optimize(pbs.Y, F0s, V0s, pbs.confounder, None, trs, tes, 0, 8, 3.0, 3.0, 0.4, 1, 1e-12, 1e-5, 11, r_seed=42)
+            oracle.set_threads(team)
+            dv = float(np.abs(Vr - ro.column_factor).max() / np.abs(ro.column_factor).max())
+            port_check = {"shape": "80x120 K=8, 12 masked elastic-net iterations, same R stream", "max_rel_diff_V": dv,
+                          "rel_diff_loss": abs(lr - ro.loss) / abs(ro.loss), "ok": bool(dv < 1e-10)}
+    except Exception as e:  # noqa: BLE001
+        port_check = {"error": str(e)[:200]}
     line = {"impl": "reference", "metric": "als_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_for(args, w),
             "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": team, "host_cpus": os.cpu_count(), "kind": "port", "sample": sample,
                              "extrapolated": P != w["P"], "sample_seconds": secs, "wall_seconds_incl_setup": wall, "build": flags,
                              "cd_sweeps_per_gene_iter": r.cd_sweeps / P / args.steps, "loss_after_timed": r.loss},
-            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "port_vs_reference_sources": port_check}
     print(json.dumps(line), flush=True)
 
 

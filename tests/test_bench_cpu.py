@@ -26,6 +26,8 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["extrapolated"] is True and "96 of 44477" in cb["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    pc = d["port_vs_reference_sources"]                    # the timed port against the reference's own sources (oracle/_ref), when present
+    assert pc is None or pc.get("ok") is True, pc
 
 
 def test_reference_arm_uses_an_explicit_openmp_team_under_a_launcher():

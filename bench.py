@@ -166,7 +166,11 @@ def run_reference(args, w, rank):
                              "extrapolated": P != w["P"], "sample_seconds": secs, "wall_seconds_incl_setup": wall, "build": flags,
                              "cd_sweeps_per_gene_iter": r.cd_sweeps / P / args.steps, "loss_after_timed": r.loss},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "port_vs_reference_sources": port_check}
+            "port_vs_reference_sources": port_check,
+            "why_the_port_is_timed": "oracle/_ref (the reference's own sources) is built serial, because the reference draws randperm from one global RNG "
+                                     "inside its OpenMP loops, and on an API shim whose products / views copy where Armadillo + BLAS do not: timing it would "
+                                     "understate the reference. The OpenMP port is the faster, i.e. the conservative, CPU arm; port_vs_reference_sources "
+                                     "shows that it computes what the reference's code computes."}
     print(json.dumps(line), flush=True)
 
 

@@ -41,6 +41,23 @@ def compare(pb, tr, te, F0, V0, K, lam, alpha, tuning, iters, X=None, gtol=1e-12
     return ro
 
 
+def test_compiled_sources_are_the_reference_files_unmodified():
+    """oracle/ref_shim/SOURCES.sha256 records which files of the reference checkout oracle/_ref is compiled from (oracle/Makefile compiles them
+    in place); where the checkout is present their hashes must match - nothing is patched, copied or pre-processed."""
+    import hashlib
+    import os
+    src = os.path.join(ref.REFERENCE, "src")
+    if not os.path.isdir(src):
+        pytest.skip("reference checkout not present (the library was built where it is)")
+    listed = [ln.split() for ln in open(os.path.join(os.path.dirname(ref.__file__), "ref_shim", "SOURCES.sha256")) if ln.strip()]
+    assert {os.path.basename(n) for _, n in listed} >= {"optimize.cpp", "coordinate_descent.cpp", "utils.cpp"}
+    for digest, name in listed:
+        with open(os.path.normpath(os.path.join(src, name)), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, name
+    mk = open(os.path.join(os.path.dirname(ref.__file__), "Makefile")).read()
+    assert "$(REF)/src/optimize.cpp" in mk and "$(REF)/src/coordinate_descent.cpp" in mk and "$(REF)/src/utils.cpp" in mk
+
+
 def test_r_rng_known_answers_in_the_shim():
     # set.seed(123); runif(3) in R
     assert np.allclose(ref.r_unif(123, 3), [0.2875775201246142, 0.7883051354438066, 0.4089769218116999], rtol=0, atol=1e-15)

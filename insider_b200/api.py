@@ -154,11 +154,17 @@ def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None
     communication. Each point draws its initial factors from a generator seeded by (seed, phase, point index), so the
     results do not depend on how points are scheduled (the reference uses whatever R's RNG stream holds at that moment).
     """
-    ld = np.atleast_1d(latent_dimension) if latent_dimension is not None else np.array([], dtype=int)
-    lam = np.atleast_1d(np.asarray(lambda_, dtype=float))
-    alp = np.atleast_1d(np.asarray(alpha, dtype=float))
+    type_msg = "TUNNING: The element of latent_dimension, lambda, and alpha should be integer, numeric, and numeric."
+    if latent_dimension is None:                                  # :83 is.integer(NULL) is FALSE
+        raise ValueError(type_msg)
+    ld = np.atleast_1d(latent_dimension)
+    try:
+        lam = np.atleast_1d(np.asarray(lambda_, dtype=float))
+        alp = np.atleast_1d(np.asarray(alpha, dtype=float))
+    except (TypeError, ValueError):
+        raise ValueError(type_msg) from None
     if not np.issubdtype(ld.dtype, np.integer):
-        raise ValueError("TUNNING: The element of latent_dimension, lambda, and alpha should be integer, numeric, and numeric.")
+        raise ValueError(type_msg)
     if len(ld) <= 1 and (len(lam) <= 1 and len(alp) <= 1):
         raise ValueError("TUNNING: The length of either latent_dimension or lambda and alpha should be greater than 1.")
     ctx_list = list(ctxs) if ctxs else [ctx or default_context()]

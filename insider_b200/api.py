@@ -201,7 +201,7 @@ def tune(obj, latent_dimension=None, lambda_=0.1, alpha=0.0, *, seed=0, ctx=None
             rank_tuning = np.array([[pt[0], f["train_rmse"], f["test_rmse"]] for pt, f in zip(pts, fitted)], dtype=float)
             if write_csv:
                 np.savetxt("insider_rank_tuning_result.csv", rank_tuning, delimiter=",", header="rank,train_rmse,test_rmse", comments="")
-        latent_rank = int(ld[np.argmin(rank_tuning[:, 2])]) if len(ld) > 1 else int(ld[0])   # :135-139
+        latent_rank = int(ld[np.nanargmin(rank_tuning[:, 2])]) if len(ld) > 1 else int(ld[0])   # :135-139 which.min skips NA
         if len(lam) > 1 or len(alp) > 1:                          # :142-174, expand.grid: lambda varies fastest
             pts = []
             for a0 in alp:

@@ -125,8 +125,8 @@ def test_tune_two_phase_grid_follows_the_reference(monkeypatch, tmp_path, capsys
     monkeypatch.chdir(tmp_path)
     capsys.readouterr()
 
-    def rmse(K, lam, alpha):                       # two ranks tie for the best test RMSE: which.min takes the first
-        return 1.0 / K, {4: 0.9, 6: 0.5, 8: 0.5, 10: 0.7}[K] + 0.01 * lam + 0.1 * abs(alpha - 0.3)
+    def rmse(K, lam, alpha):                       # two ranks tie for the best test RMSE: which.min takes the first (and skips NA)
+        return 1.0 / K, {4: float("nan"), 6: 0.5, 8: 0.5, 10: 0.7}[K] + 0.01 * lam + 0.1 * abs(alpha - 0.3)
 
     calls, residents = _fake_backend(monkeypatch, rmse)
     lam, alp = [1.004, 3.0, 5.126], [0.2, 0.3]

@@ -384,7 +384,9 @@ def run_ours(args, w, rank, world, local):
                   "share_of_iteration": kern[cd_name]["share"], "ms_per_step": kern[cd_name]["ms_per_step"]}
         roof_dom = None
         if cd:
-            roof_dom = {"bound": "fp64", "limiter": "FP64 CUDA-core pipe (DFMA chain, no tensor-core form); see DESIGN.md 4 for the ncu reading",
+            roof_dom = {"bound": "fp64", "limiter": "FP64 work on the CUDA cores (DFMA chain, no tensor-core form), held below the FP64 peak by the shared-memory data "
+                                                    "pipe: l1tex 89 % busy with the broadcast loads of the XtX row, FP64 pipe 40 % (ncu, profiles/"
+                                                    "r02_ncu_k_cd_dense_pform_dense_A.txt), and by the lone-warp tail of the longest genes; DESIGN.md 4",
                         "kernel": cd_name, "achieved": cd["fp64_tflops"], "peak": FP64_PEAK,
                         "unit": "TFLOP/s", "frac": cd["fp64_tflops"] / FP64_PEAK,
                         # dram__bytes_read + write of ONE launch from the committed ncu --set full capture (not measured in this run)

@@ -20,6 +20,7 @@ tune_b200 <- function(object, latent_dimension = NULL, lambda = 0.1, alpha = 0.0
     rank_tuning <- NULL; reg_tuning <- NULL
     if(length(latent_dimension) > 1){
         for(latent_rank in latent_dimension){
+            cat('Latent rank: ', latent_rank, "---------------------------------\n")
             f <- init(latent_rank)
             hp <- if(length(lambda) == 1 & length(alpha) == 1) c(lambda, lambda, alpha) else c(0.1, 0.1, 0)
             fitted <- b200_optimize_resident(h, f[[1]], f[[2]], latent_rank, hp[1], hp[2], hp[3], 1, p[['global_tol']], p[['sub_tol']], p[['tuning_iter']])
@@ -31,6 +32,7 @@ tune_b200 <- function(object, latent_dimension = NULL, lambda = 0.1, alpha = 0.0
     if(length(lambda) > 1 | length(alpha) > 1){
         param_grid <- expand.grid(lambda = lambda, alpha = alpha)
         for(i in seq(nrow(param_grid))){
+            cat('parameter grid:', paste(round(param_grid[i,], 2), collapse = ','), "---------------------------------\n")
             l <- round(param_grid[i, 1], 2); a <- round(param_grid[i, 2], 2)
             f <- init(latent_rank)
             fitted <- b200_optimize_resident(h, f[[1]], f[[2]], latent_rank, l, l, a, 1, p[['global_tol']], p[['sub_tol']], p[['tuning_iter']])
